@@ -1,0 +1,56 @@
+// gemm_nt.cuh -- host-side descriptor of the FP64 "NT" GEMM family used by every O(N^3) phase:
+//     C[m,n] (+)= alpha * sum_{k in [klo,khi)} A[m,k] * B[n,k]          (all row-major)
+// Cholesky trailing update (SYRK), panel TRSM through inverted diagonal blocks, the level-parallel
+// triangular inverse, the LAUUM-like W'W product and the predictive TRSM are all instances.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum : int {
+    GEMM_LOWER_ONLY = 1,   // square output, only tiles bm >= bn; diagonal tiles write i >= j only
+    GEMM_KLO_M      = 2,   // k starts at bm*128        (A rows are upper-triangular in the frame)
+    GEMM_KHI_M      = 4,   // k ends at (bm+1)*128      (A rows are lower-triangular)
+    GEMM_KHI_N      = 8,   // k ends at (bn+1)*128      (B rows are lower-triangular)
+};
+
+// A matrix living in a handle-owned buffer.  `map` is the TMA descriptor of the whole buffer
+// (box 16 x 128 doubles, 128B swizzle); `base/ld` the same buffer for the non-TMA kernel.
+struct GemmBuf {
+    const CUtensorMap* map;
+    const double* base;
+    int64_t ld;
+};
+
+struct GemmOperand {
+    GemmBuf buf;        // main buffer
+    GemmBuf sub;        // compact [Npad x 128] buffer of clean diagonal tiles (or map == nullptr)
+    int row0, col0;     // origin of the operand inside the buffer frame (multiples of 128)
+};
+
+struct GemmDesc {
+    GemmOperand A, B;
+    double* C; int64_t ldc; int c_row0, c_col0;
+    double* Ct; int64_t ldct; int ct_row0, ct_col0;    // optional transposed copy: Ct[n, m] = C[m, n]
+    int M, N, K;                                       // multiples of 128, 128, 16
+    double alpha, beta;
+    int flags;
+    int batch;          // grid.z
+    int zstep;          // added to every row0/col0 per batch index (diagonal stepping)
+    int m_lim, n_lim, k_lim;   // per-batch clipping: M_z = min(M, m_lim - z*zstep) etc. (<=0: skip)
+};
+
+static inline GemmDesc gemm_desc_default() {
+    GemmDesc d{};
+    d.alpha = 1.0; d.beta = 0.0; d.batch = 1; d.zstep = 0;
+    d.m_lim = d.n_lim = d.k_lim = 1 << 30;
+    return d;
+}
+
+// impl: 0 = TMA + mbarrier warp-specialised kernel, 1 = simple synchronous kernel.
+cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream);
+// one-time per process (sets max dynamic smem)
+cudaError_t gemm_nt_init();
+// Build a TMA descriptor for a row-major [rows x cols] FP64 buffer, box 16 x 128, swizzle 128B.
+// Returns false (and leaves *out zeroed) if the driver entry point is unavailable.
+bool gemm_make_tensor_map(CUtensorMap* out, const double* base, int64_t rows, int64_t cols, int64_t ld);

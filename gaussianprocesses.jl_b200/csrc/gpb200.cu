@@ -1,0 +1,743 @@
+// gpb200.cu -- the engine behind the C ABI of include/gpb200.h: device state, the blocked
+// factorisation / inverse schedules, and the entry points the reference-side shim binds.
+//
+// Device layout (all FP64, row-major, leading dimension Npad = N rounded up to 128; the padding is
+// an identity block, so L, L^-1, logdet and every solve are unaffected):
+//   F     Npad x Npad   lower triangle: L (K_y = L L'; the reference's U = L', src/GP.jl:110).
+//                       strict-upper tiles: scratch for the triangular-inverse merges.
+//   G     Npad x Npad   lower tiles: K_y -> Schur complements during the factorisation ->
+//                       W = L^-1 (strictly-lower tiles) ; strictly-upper tiles: W' ;
+//                       after gpb200_grad_prepare the lower triangle holds K_y^-1.
+//   Dinv / DinvT  Npad x 128   clean lower / upper copies of the inverted diagonal tiles.
+//   x     N x d point-major (== Julia's d x N column-major), uploaded once (gpb200_set_data).
+// The reference keeps four N x N host matrices per GPE (R, cK.mat, chol factors, ααinvcKI;
+// test/memory.jl:14-19); this engine keeps two on the device and no distance cache.
+//
+// Every O(N^3) step is the NT DMMA GEMM of gemm_nt.cu:
+//   Cholesky (right-looking, outer block nb): leaf potrf128 (+ tile inverse) -> panel TRSM as a
+//   GEMM against the inverted diagonal block -> trailing SYRK.  The inverse of each nb x nb
+//   diagonal block is assembled on the way by the same merges the full inverse uses.
+//   Inverse: bottom-up *level-parallel* triangular inverse -- at level s every pair of adjacent
+//   s x s diagonal blocks is merged independently, W21 = -W_C (L21 W_A), two batched GEMMs per
+//   level, 2 log2(Npad/nb) launches in total -- then K_y^-1 = W' W in ONE triangular SYRK launch.
+//   N^3/3 + 2N^3/3 = N^3 flop per mll+gradient (the reference's potrs on the identity costs 7N^3/3).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gpb200.h"
+#include "gemm_nt.cuh"
+#include "gram.cuh"
+#include "kprog.cuh"
+#include "potrf_base.cuh"
+#include "vec.cuh"
+
+namespace {
+constexpr int TILE = 128;
+constexpr double LOG2PI = 1.8378770664093453;
+std::string g_create_error;
+}  // namespace
+
+struct gpb200_handle {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    int64_t N = 0, Npad = 0, ld = 0;
+    int d = 0;
+    double* x = nullptr;
+    KProg prog{};
+    std::vector<double> theta;
+    bool has_data = false, has_kernel = false, factored = false, inv_ready = false, alpha_ready = false;
+    double *F = nullptr, *G = nullptr, *Dinv = nullptr, *DinvT = nullptr, *logd = nullptr;
+    double *noise_var = nullptr, *r0 = nullptr, *r1 = nullptr, *y1 = nullptr, *alpha = nullptr, *scal = nullptr;
+    double *part = nullptr, *trace_out = nullptr;
+    int* info_dev = nullptr;
+    int64_t n_noise = 1;
+    double nugget = 0.0;
+    CUtensorMap mapF{}, mapG{}, mapDinv{}, mapDinvT{};
+    bool tma_ok = false;
+    // predict workspace
+    double *xs = nullptr, *Kst = nullptr, *Kss = nullptr, *pmu = nullptr, *pvar = nullptr, *pkdiag = nullptr;
+    int64_t xs_cap = 0, Kst_rows = 0, Kss_rows = 0;
+    CUtensorMap mapKst{};
+    // options
+    int nb = 512;
+    int gemm_impl = 0;
+    int lookahead = 0;
+    // stats
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,       \
+                     cudaGetErrorString(e_));                                                      \
+            h->err = buf_;                                                                         \
+            (void)cudaGetLastError();                                                              \
+            return GPB200_ECUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int fail(gpb200_handle* h, int code, const char* msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+void free_data(gpb200_handle* h) {
+    double** ptrs[] = {&h->x, &h->F, &h->G, &h->Dinv, &h->DinvT, &h->logd, &h->noise_var, &h->r0, &h->r1,
+                       &h->y1, &h->alpha, &h->scal, &h->part, &h->trace_out, &h->xs, &h->Kst, &h->Kss,
+                       &h->pmu, &h->pvar, &h->pkdiag};
+    for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
+    h->xs_cap = h->Kst_rows = h->Kss_rows = 0;
+    h->has_data = h->factored = h->inv_ready = h->alpha_ready = false;
+}
+
+GemmBuf bufF(gpb200_handle* h) { return GemmBuf{h->tma_ok ? &h->mapF : nullptr, h->F, h->ld}; }
+GemmBuf bufG(gpb200_handle* h) { return GemmBuf{h->tma_ok ? &h->mapG : nullptr, h->G, h->ld}; }
+GemmBuf bufDinv(gpb200_handle* h) { return GemmBuf{h->tma_ok ? &h->mapDinv : nullptr, h->Dinv, TILE}; }
+GemmBuf bufDinvT(gpb200_handle* h) { return GemmBuf{h->tma_ok ? &h->mapDinvT : nullptr, h->DinvT, TILE}; }
+GemmBuf bufNone() { return GemmBuf{nullptr, nullptr, 0}; }
+
+cudaError_t launch_gemm(gpb200_handle* h, const GemmDesc& d) {
+    ++h->launches;
+    return gemm_nt_launch(d, h->tma_ok ? h->gemm_impl : 1, h->st);
+}
+
+// ---- pieces of the factorisation --------------------------------------------------------------
+
+// F[r0.., p..p+n) = G[r0.., p..p+n) * W(p,n)'     (panel TRSM through the inverted diagonal block)
+cudaError_t panel_trsm(gpb200_handle* h, int r0, int rows, int p, int n) {
+    GemmDesc g = gemm_desc_default();
+    g.A = GemmOperand{bufG(h), bufNone(), r0, p};
+    g.B = GemmOperand{bufG(h), bufDinv(h), p, p};
+    g.C = h->F; g.ldc = h->ld; g.c_row0 = r0; g.c_col0 = p;
+    g.M = rows; g.N = n; g.K = n;
+    g.flags = GEMM_KHI_N;
+    return launch_gemm(h, g);
+}
+// G[r0.., r0..) -= F[r0.., p..p+n) F[r0.., p..p+n)'   (lower tiles)
+cudaError_t trailing_syrk(gpb200_handle* h, int r0, int rows, int p, int n) {
+    GemmDesc g = gemm_desc_default();
+    g.A = GemmOperand{bufF(h), bufNone(), r0, p};
+    g.B = GemmOperand{bufF(h), bufNone(), r0, p};
+    g.C = h->G; g.ldc = h->ld; g.c_row0 = r0; g.c_col0 = r0;
+    g.M = rows; g.N = rows; g.K = n;
+    g.alpha = -1.0; g.beta = 1.0;
+    g.flags = GEMM_LOWER_ONLY;
+    return launch_gemm(h, g);
+}
+// merge of the inverses of two adjacent diagonal blocks [p,p+n1) and [p+n1,p+n1+n2):
+//   T' = Wt_A * L21'  -> F strict-upper block (p, p+n1)
+//   W21 = -W_C * T    -> G (p+n1, p)  and its transpose -> G (p, p+n1)
+// batched over `batch` problems stepping 2*n1 along the diagonal (clipped at Npad).
+cudaError_t merge_inverse(gpb200_handle* h, int p, int n1, int n2, int batch) {
+    const int lim = (int)h->Npad - p - n1;     // rows available below the first block of problem 0
+    {
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bufG(h), bufDinvT(h), p, p};
+        g.B = GemmOperand{bufF(h), bufNone(), p + n1, p};
+        g.C = h->F; g.ldc = h->ld; g.c_row0 = p; g.c_col0 = p + n1;
+        g.M = n1; g.N = n2; g.K = n1;
+        g.flags = GEMM_KLO_M;
+        g.batch = batch; g.zstep = 2 * n1;
+        g.n_lim = lim;
+        cudaError_t e = launch_gemm(h, g);
+        if (e != cudaSuccess) return e;
+    }
+    {
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bufG(h), bufDinv(h), p + n1, p + n1};
+        g.B = GemmOperand{bufF(h), bufNone(), p, p + n1};
+        g.C = h->G; g.ldc = h->ld; g.c_row0 = p + n1; g.c_col0 = p;
+        g.Ct = h->G; g.ldct = h->ld; g.ct_row0 = p; g.ct_col0 = p + n1;
+        g.M = n2; g.N = n1; g.K = n2;
+        g.alpha = -1.0;
+        g.flags = GEMM_KHI_M;
+        g.batch = batch; g.zstep = 2 * n1;
+        g.m_lim = lim; g.k_lim = lim;
+        return launch_gemm(h, g);
+    }
+}
+
+// factor the diagonal block [p, p+n) (n <= s, s = 128 * 2^k, p aligned to s) and assemble its inverse
+cudaError_t potrf_block(gpb200_handle* h, int p, int n, int s) {
+    cudaError_t e;
+    if (s == TILE) {
+        ++h->launches;
+        return potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st);
+    }
+    const int hs = s / 2;
+    if (n <= hs) return potrf_block(h, p, n, hs);
+    if ((e = potrf_block(h, p, hs, hs)) != cudaSuccess) return e;
+    const int n2 = n - hs;
+    if ((e = panel_trsm(h, p + hs, n2, p, hs)) != cudaSuccess) return e;
+    if ((e = trailing_syrk(h, p + hs, n2, p, hs)) != cudaSuccess) return e;
+    if ((e = potrf_block(h, p + hs, n2, hs)) != cudaSuccess) return e;
+    return merge_inverse(h, p, hs, n2, 1);
+}
+
+cudaError_t cholesky(gpb200_handle* h) {
+    const int Np = (int)h->Npad;
+    cudaError_t e;
+    for (int p = 0; p < Np; p += h->nb) {
+        const int n = (Np - p < h->nb) ? Np - p : h->nb;
+        if ((e = potrf_block(h, p, n, h->nb)) != cudaSuccess) return e;
+        const int rem = Np - p - n;
+        if (rem > 0) {
+            if ((e = panel_trsm(h, p + n, rem, p, n)) != cudaSuccess) return e;
+            if ((e = trailing_syrk(h, p + n, rem, p, n)) != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
+}
+
+// remaining levels of the triangular inverse (blocks of size nb are already inverted), then W'W
+cudaError_t inverse_from_factor(gpb200_handle* h) {
+    const int Np = (int)h->Npad;
+    cudaError_t e;
+    for (long long s = h->nb; s < Np; s *= 2) {
+        const int batch = (int)((Np + 2 * s - 1) / (2 * s));
+        const int n2 = (int)((Np - s < s) ? Np - s : s);
+        if ((e = merge_inverse(h, 0, (int)s, n2, batch)) != cudaSuccess) return e;
+    }
+    GemmDesc g = gemm_desc_default();
+    g.A = GemmOperand{bufG(h), bufDinvT(h), 0, 0};
+    g.B = GemmOperand{bufG(h), bufDinvT(h), 0, 0};
+    g.C = h->G; g.ldc = h->ld; g.c_row0 = 0; g.c_col0 = 0;
+    g.M = Np; g.N = Np; g.K = Np;
+    g.flags = GEMM_LOWER_ONLY | GEMM_KLO_M;
+    return launch_gemm(h, g);
+}
+
+// alpha-type solve on device vectors: out = K_y^-1 rhs ; rhs (Npad, zero padded) is destroyed
+cudaError_t solve_device(gpb200_handle* h, double* rhs, double* tmp, double* out) {
+    cudaError_t e = trsv_lower_fwd(h->F, h->ld, h->Dinv, rhs, tmp, h->Npad, h->st, &h->launches);
+    if (e != cudaSuccess) return e;
+    return trsv_lower_bwd(h->F, h->ld, h->DinvT, tmp, out, h->Npad, h->st, &h->launches);
+}
+
+int upload_padded(gpb200_handle* h, double* dst, const double* src_host) {
+    CK(cudaMemsetAsync(dst, 0, sizeof(double) * h->Npad, h->st));
+    CK(cudaMemcpyAsync(dst, src_host, sizeof(double) * h->N, cudaMemcpyHostToDevice, h->st));
+    return GPB200_OK;
+}
+
+int ensure_predict_ws(gpb200_handle* h, int64_t Mc, bool want_cov) {
+    const int64_t Mpad = (Mc + TILE - 1) / TILE * TILE;
+    if (Mpad > h->xs_cap) {
+        if (h->xs) cudaFree(h->xs);
+        if (h->pmu) cudaFree(h->pmu);
+        if (h->pvar) cudaFree(h->pvar);
+        if (h->pkdiag) cudaFree(h->pkdiag);
+        h->xs = h->pmu = h->pvar = h->pkdiag = nullptr; h->xs_cap = 0;
+        CK(cudaMalloc(&h->xs, sizeof(double) * Mpad * h->d));
+        CK(cudaMalloc(&h->pmu, sizeof(double) * Mpad));
+        CK(cudaMalloc(&h->pvar, sizeof(double) * Mpad));
+        CK(cudaMalloc(&h->pkdiag, sizeof(double) * Mpad));
+        h->xs_cap = Mpad;
+    }
+    if (Mpad > h->Kst_rows) {
+        if (h->Kst) cudaFree(h->Kst);
+        h->Kst = nullptr; h->Kst_rows = 0;
+        CK(cudaMalloc(&h->Kst, sizeof(double) * Mpad * h->Npad));
+        h->Kst_rows = Mpad;
+        if (h->tma_ok && !gemm_make_tensor_map(&h->mapKst, h->Kst, Mpad, h->Npad, h->Npad))
+            return fail(h, GPB200_ECUDA, "cuTensorMapEncodeTiled failed for the predict buffer");
+    }
+    if (want_cov && Mpad > h->Kss_rows) {
+        if (h->Kss) cudaFree(h->Kss);
+        h->Kss = nullptr; h->Kss_rows = 0;
+        CK(cudaMalloc(&h->Kss, sizeof(double) * Mpad * Mpad));
+        h->Kss_rows = Mpad;
+    }
+    return GPB200_OK;
+}
+
+// Vt[:, c0..c0+n) <- solve against L[c0.., c0..] in place on the predict buffer (rows = Mpad):
+// recursive blocked TRSM, leaves multiply by the inverted 128-tile, updates are NT GEMMs.
+cudaError_t trsm_rec(gpb200_handle* h, int Mpad, int c0, int n) {
+    GemmBuf bk{h->tma_ok ? &h->mapKst : nullptr, h->Kst, h->Npad};
+    if (n == TILE) {
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bk, bufNone(), 0, c0};
+        g.B = GemmOperand{bufDinv(h), bufNone(), c0, 0};
+        g.C = h->Kst; g.ldc = h->Npad; g.c_row0 = 0; g.c_col0 = c0;
+        g.M = Mpad; g.N = TILE; g.K = TILE;
+        return launch_gemm(h, g);
+    }
+    int n1 = TILE;
+    while (n1 * 2 < n) n1 *= 2;
+    const int n2 = n - n1;
+    cudaError_t e;
+    if ((e = trsm_rec(h, Mpad, c0, n1)) != cudaSuccess) return e;
+    {
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bk, bufNone(), 0, c0};
+        g.B = GemmOperand{bufF(h), bufNone(), c0 + n1, c0};
+        g.C = h->Kst; g.ldc = h->Npad; g.c_row0 = 0; g.c_col0 = c0 + n1;
+        g.M = Mpad; g.N = n2; g.K = n1;
+        g.alpha = -1.0; g.beta = 1.0;
+        if ((e = launch_gemm(h, g)) != cudaSuccess) return e;
+    }
+    return trsm_rec(h, Mpad, c0 + n1, n2);
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int gpb200_version(void) { return 100; }
+
+const char* gpb200_last_error(gpb200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gpb200_create(gpb200_handle** out, int device) {
+    if (!out) return GPB200_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                         "); libgpb200 has no CPU fallback";
+        (void)cudaGetLastError();
+        return GPB200_ECUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "device index out of range"; return GPB200_EINVAL; }
+    gpb200_handle* h = new gpb200_handle();
+    h->device = device;
+    auto bail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete h;
+        return GPB200_ECUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+    if ((e = gemm_nt_init()) != cudaSuccess) return bail("gemm_nt_init", e);
+    const char* env = getenv("GPB200_GEMM");
+    if (env) h->gemm_impl = atoi(env);
+    env = getenv("GPB200_NB");
+    if (env) { int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048) h->nb = v; }
+    *out = h;
+    return GPB200_OK;
+}
+
+void gpb200_destroy(gpb200_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    free_data(h);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
+    if (!h || !key) return GPB200_EINVAL;
+    if (!strcmp(key, "nb")) {
+        if (value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048)
+            return fail(h, GPB200_EINVAL, "nb must be 128, 256, 512, 1024 or 2048");
+        h->nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
+    }
+    if (!strcmp(key, "gemm")) { h->gemm_impl = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
+    return fail(h, GPB200_EINVAL, "unknown option");
+}
+
+int64_t gpb200_launch_count(gpb200_handle* h) { return h ? h->launches : 0; }
+
+int gpb200_get_timings(gpb200_handle* h, double* ms, int32_t n) {
+    if (!h || !ms) return GPB200_EINVAL;
+    for (int i = 0; i < n && i < 8; ++i) ms[i] = h->ms[i];
+    return GPB200_OK;
+}
+
+int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int64_t ldx) {
+    if (!h) return GPB200_EINVAL;
+    if (N <= 0 || d <= 0 || !x || ldx < d) return fail(h, GPB200_EINVAL, "set_data: bad N, d, x or ldx");
+    if (d > GPB200_MAX_DIMS) return fail(h, GPB200_EINVAL, "set_data: d exceeds GPB200_MAX_DIMS");
+    if (N > (int64_t)1 << 30) return fail(h, GPB200_EINVAL, "set_data: N too large");
+    CK(cudaSetDevice(h->device));
+    const int64_t Npad = (N + TILE - 1) / TILE * TILE;
+    const bool realloc = !h->has_data || Npad != h->Npad || d != h->d;
+    if (realloc) {
+        free_data(h);
+        h->N = N; h->Npad = Npad; h->ld = Npad; h->d = d;
+        const size_t nn = sizeof(double) * (size_t)Npad * (size_t)Npad;
+        CK(cudaMalloc(&h->x, sizeof(double) * N * d));
+        CK(cudaMalloc(&h->F, nn));
+        CK(cudaMalloc(&h->G, nn));
+        CK(cudaMalloc(&h->Dinv, sizeof(double) * Npad * TILE));
+        CK(cudaMalloc(&h->DinvT, sizeof(double) * Npad * TILE));
+        const size_t nv = sizeof(double) * Npad;
+        CK(cudaMalloc(&h->logd, nv)); CK(cudaMalloc(&h->noise_var, nv)); CK(cudaMalloc(&h->r0, nv));
+        CK(cudaMalloc(&h->r1, nv)); CK(cudaMalloc(&h->y1, nv)); CK(cudaMalloc(&h->alpha, nv));
+        CK(cudaMalloc(&h->scal, sizeof(double) * 16));
+        CK(cudaMalloc(&h->info_dev, sizeof(int)));
+        const int64_t T = Npad / TILE;
+        CK(cudaMalloc(&h->part, sizeof(double) * (size_t)(T * (T + 1) / 2) * (GPB200_MAX_THETA + 1)));
+        CK(cudaMalloc(&h->trace_out, sizeof(double) * (GPB200_MAX_THETA + 1)));
+        CK(cudaMemsetAsync(h->F, 0, nn, h->st));
+        CK(cudaMemsetAsync(h->G, 0, nn, h->st));
+        h->tma_ok = gemm_make_tensor_map(&h->mapF, h->F, Npad, Npad, Npad) &&
+                    gemm_make_tensor_map(&h->mapG, h->G, Npad, Npad, Npad) &&
+                    gemm_make_tensor_map(&h->mapDinv, h->Dinv, Npad, TILE, TILE) &&
+                    gemm_make_tensor_map(&h->mapDinvT, h->DinvT, Npad, TILE, TILE);
+    }
+    h->N = N;
+    // x arrives as Julia's d x N column-major (ld = ldx): point i is the contiguous run x[i*ldx .. +d)
+    CK(cudaMemcpy2DAsync(h->x, sizeof(double) * d, x, sizeof(double) * ldx, sizeof(double) * d, N,
+                         cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->has_data = true;
+    h->factored = h->inv_ready = h->alpha_ready = false;
+    return GPB200_OK;
+}
+
+int gpb200_set_kernel(gpb200_handle* h, int32_t n_ops, const int32_t* ops, int32_t n_dims, const int32_t* dims,
+                      int32_t n_theta) {
+    if (!h) return GPB200_EINVAL;
+    if (n_ops <= 0 || n_ops > GPB200_MAX_OPS || !ops) return fail(h, GPB200_EINVAL, "set_kernel: bad n_ops");
+    if (n_theta < 0 || n_theta > GPB200_MAX_THETA) return fail(h, GPB200_EINVAL, "set_kernel: too many parameters");
+    if (n_dims < 0 || n_dims > GPB200_MAX_DIMS || (n_dims > 0 && !dims)) return fail(h, GPB200_EINVAL, "set_kernel: bad dims");
+    KProg P{};
+    P.n_ops = n_ops; P.n_theta = n_theta;
+    int stack[GPB200_MAX_OPS]; int sp = 0; int tcount = 0;
+    for (int q = 0; q < n_ops; ++q) {
+        const int32_t* o = ops + q * GPB200_OP_STRIDE;
+        P.op[q] = o[0]; P.toff[q] = o[1]; P.nth[q] = o[2]; P.doff[q] = o[3]; P.nd[q] = o[4]; P.extra[q] = o[5];
+        if (o[0] == GPB200_OP_SUM || o[0] == GPB200_OP_PROD) {
+            if (sp < 2) return fail(h, GPB200_EINVAL, "set_kernel: malformed program (stack underflow)");
+            const int right = stack[--sp]; const int left = stack[--sp];
+            if (right != q - 1) return fail(h, GPB200_EINVAL, "set_kernel: program is not in post-order");
+            P.left[q] = left; P.nth[q] = 0;
+            stack[sp++] = q;
+        } else {
+            if (o[0] < GPB200_OP_SE_ISO || o[0] > GPB200_OP_CONST) return fail(h, GPB200_EINVAL, "set_kernel: unknown opcode");
+            if (o[1] < 0 || o[2] < 0 || o[1] + o[2] > n_theta) return fail(h, GPB200_EINVAL, "set_kernel: theta range");
+            if (o[3] < 0 || o[4] < 0 || o[3] + o[4] > n_dims) return fail(h, GPB200_EINVAL, "set_kernel: dims range");
+            int expect = -1;
+            switch (o[0]) {
+            case GPB200_OP_SE_ISO: case GPB200_OP_MAT12_ISO: case GPB200_OP_MAT32_ISO: case GPB200_OP_MAT52_ISO:
+            case GPB200_OP_POLY: expect = 2; break;
+            case GPB200_OP_SE_ARD: case GPB200_OP_MAT12_ARD: case GPB200_OP_MAT32_ARD: case GPB200_OP_MAT52_ARD:
+                expect = o[4] + 1; break;
+            case GPB200_OP_RQ_ISO: case GPB200_OP_PERIODIC: expect = 3; break;
+            case GPB200_OP_RQ_ARD: expect = o[4] + 2; break;
+            case GPB200_OP_LIN_ISO: case GPB200_OP_NOISE: case GPB200_OP_CONST: expect = 1; break;
+            case GPB200_OP_LIN_ARD: expect = o[4]; break;
+            }
+            if (o[2] != expect) return fail(h, GPB200_EINVAL, "set_kernel: wrong parameter count for a leaf");
+            tcount += o[2];
+            stack[sp++] = q;
+        }
+    }
+    if (sp != 1 || tcount != n_theta) return fail(h, GPB200_EINVAL, "set_kernel: malformed program");
+    for (int i = 0; i < n_dims; ++i) {
+        if (dims[i] < 0 || (h->has_data && dims[i] >= h->d)) return fail(h, GPB200_EINVAL, "set_kernel: dim index out of range");
+        P.dims[i] = dims[i];
+    }
+    // single SEIso leaf over dims 0..nd-1 == the whole input: specialised kernels
+    P.fast = 0;
+    if (n_ops == 1 && P.op[0] == GPB200_OP_SE_ISO && h->has_data && P.nd[0] == h->d) {
+        bool ident = true;
+        for (int i = 0; i < P.nd[0]; ++i) ident = ident && (P.dims[P.doff[0] + i] == i);
+        P.fast = ident ? 1 : 0;
+    }
+    h->prog = P;
+    h->theta.assign(n_theta, 0.0);
+    h->has_kernel = true;
+    h->factored = h->inv_ready = false;
+    return GPB200_OK;
+}
+
+int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_noise, int64_t n_noise,
+                     double extra_nugget) {
+    if (!h) return GPB200_EINVAL;
+    if (!h->has_data || !h->has_kernel) return fail(h, GPB200_ESTATE, "factorize: set_data and set_kernel first");
+    if ((h->prog.n_theta > 0 && !theta) || !log_noise) return fail(h, GPB200_EINVAL, "factorize: null theta/log_noise");
+    if (n_noise != 1 && n_noise != h->N) return fail(h, GPB200_EINVAL, "factorize: n_noise must be 1 or N");
+    for (int i = 0; i < h->prog.n_theta; ++i)
+        if (!isfinite(theta[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite hyper-parameter");
+    CK(cudaSetDevice(h->device));
+    h->factored = h->inv_ready = h->alpha_ready = false;
+    for (int i = 0; i < h->prog.n_theta; ++i) h->theta[i] = theta[i];
+    kprog_set_theta(h->prog, theta);
+    std::vector<double> nv((size_t)n_noise);
+    for (int64_t i = 0; i < n_noise; ++i) {
+        if (!isfinite(log_noise[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite logNoise");
+        nv[i] = exp(2.0 * log_noise[i]);
+    }
+    CK(cudaMemcpyAsync(h->noise_var, nv.data(), sizeof(double) * n_noise, cudaMemcpyHostToDevice, h->st));
+    h->n_noise = n_noise; h->nugget = extra_nugget;
+    const int init = INT_MAX;
+    CK(cudaMemcpyAsync(h->info_dev, &init, sizeof(int), cudaMemcpyHostToDevice, h->st));
+
+    CK(cudaEventRecord(h->ev0, h->st));
+    ++h->launches;
+    CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld, h->st));
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cholesky(h));
+    CK(cudaEventRecord(h->ev2, h->st));
+    int info = 0;
+    CK(cudaMemcpyAsync(&info, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->ms[0] = ev_ms(h->ev0, h->ev1);
+    h->ms[1] = ev_ms(h->ev1, h->ev2);
+    if (info != INT_MAX) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "matrix is not positive definite; leading minor %d", info);
+        h->err = buf;
+        return info > h->N ? (int)h->N : info;
+    }
+    h->factored = true;
+    return GPB200_OK;
+}
+
+int gpb200_logdet(gpb200_handle* h, double* logdet) {
+    if (!h || !logdet) return GPB200_EINVAL;
+    if (!h->factored) return fail(h, GPB200_ESTATE, "logdet: factorize first");
+    CK(cudaSetDevice(h->device));
+    ++h->launches;
+    CK(sum_launch(h->logd, h->Npad, h->scal, h->st));
+    CK(cudaMemcpyAsync(logdet, h->scal, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return GPB200_OK;
+}
+
+int gpb200_solve(gpb200_handle* h, const double* rhs, double* out) {
+    if (!h || !rhs || !out) return GPB200_EINVAL;
+    if (!h->factored) return fail(h, GPB200_ESTATE, "solve: factorize first");
+    CK(cudaSetDevice(h->device));
+    int rc = upload_padded(h, h->r1, rhs);
+    if (rc) return rc;
+    CK(solve_device(h, h->r1, h->y1, h->r0));
+    CK(cudaMemcpyAsync(out, h->r0, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return GPB200_OK;
+}
+
+int gpb200_mll(gpb200_handle* h, const double* y_minus_mean, double* alpha, double* mll) {
+    if (!h || !y_minus_mean || !mll) return GPB200_EINVAL;
+    if (!h->factored) return fail(h, GPB200_ESTATE, "mll: factorize first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev0, h->st));
+    int rc = upload_padded(h, h->r0, y_minus_mean);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->r1, h->r0, sizeof(double) * h->Npad, cudaMemcpyDeviceToDevice, h->st));
+    CK(solve_device(h, h->r1, h->y1, h->alpha));
+    h->launches += 2;
+    CK(dot_launch(h->r0, h->alpha, h->Npad, h->scal + 0, h->st));
+    CK(sum_launch(h->logd, h->Npad, h->scal + 1, h->st));
+    double s[2];
+    CK(cudaMemcpyAsync(s, h->scal, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
+    if (alpha) CK(cudaMemcpyAsync(alpha, h->alpha, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->ms[2] = ev_ms(h->ev0, h->ev1);
+    *mll = -(s[0] + s[1] + LOG2PI * (double)h->N) / 2.0;    // src/GPE.jl:210
+    h->alpha_ready = true;
+    return GPB200_OK;
+}
+
+int gpb200_grad_prepare(gpb200_handle* h) {
+    if (!h) return GPB200_EINVAL;
+    if (!h->factored) return fail(h, GPB200_ESTATE, "grad_prepare: factorize first");
+    if (h->inv_ready) return GPB200_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev0, h->st));
+    CK(inverse_from_factor(h));
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->ms[3] = ev_ms(h->ev0, h->ev1);
+    h->inv_ready = true;
+    return GPB200_OK;
+}
+
+int gpb200_grad_kernel(gpb200_handle* h, const double* alpha, double* dmll_kernel, double* trA) {
+    if (!h) return GPB200_EINVAL;
+    if (!h->inv_ready) return fail(h, GPB200_ESTATE, "grad_kernel: grad_prepare first");
+    if (!alpha && !h->alpha_ready) return fail(h, GPB200_ESTATE, "grad_kernel: no alpha (call mll or pass alpha)");
+    CK(cudaSetDevice(h->device));
+    if (alpha) {
+        int rc = upload_padded(h, h->alpha, alpha);
+        if (rc) return rc;
+        h->alpha_ready = true;
+    }
+    CK(cudaEventRecord(h->ev0, h->st));
+    h->launches += 2;
+    CK(trace_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st));
+    CK(cudaEventRecord(h->ev1, h->st));
+    const int np = h->prog.n_theta;
+    std::vector<double> out((size_t)np + 1);
+    CK(cudaMemcpyAsync(out.data(), h->trace_out, sizeof(double) * (np + 1), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->ms[4] = ev_ms(h->ev0, h->ev1);
+    if (dmll_kernel) for (int p = 0; p < np; ++p) dmll_kernel[p] = out[p];
+    if (trA) *trA = out[np];
+    return GPB200_OK;
+}
+
+int gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, const double* alpha,
+                   double* mu, double* var, double* cov) {
+    if (!h) return GPB200_EINVAL;
+    if (!h->factored) return fail(h, GPB200_ESTATE, "predict: factorize first");
+    if (M <= 0 || !xs || ldxs < h->d || !mu) return fail(h, GPB200_EINVAL, "predict: bad M, xs, ldxs or mu");
+    if (!alpha && !h->alpha_ready) return fail(h, GPB200_ESTATE, "predict: no alpha (call mll or pass alpha)");
+    CK(cudaSetDevice(h->device));
+    if (alpha) {
+        int rc = upload_padded(h, h->alpha, alpha);
+        if (rc) return rc;
+        h->alpha_ready = true;
+    }
+    // chunk the test points so that the M_c x Npad workspace stays below ~16 GB
+    int64_t cap = (int64_t)(16.0e9 / (8.0 * (double)h->Npad)) / TILE * TILE;
+    if (cap < TILE) cap = TILE;
+    if (cov) cap = (M + TILE - 1) / TILE * TILE;          // full covariance needs all of V at once
+    const bool need_v = (var != nullptr) || (cov != nullptr);
+    CK(cudaEventRecord(h->ev2, h->st));
+    for (int64_t m0 = 0; m0 < M; m0 += cap) {
+        const int64_t Mc = (M - m0 < cap) ? M - m0 : cap;
+        const int64_t Mpad = (Mc + TILE - 1) / TILE * TILE;
+        int rc = ensure_predict_ws(h, Mc, cov != nullptr);
+        if (rc) return rc;
+        CK(cudaMemcpy2DAsync(h->xs, sizeof(double) * h->d, xs + m0 * ldxs, sizeof(double) * ldxs,
+                             sizeof(double) * h->d, Mc, cudaMemcpyHostToDevice, h->st));
+        h->launches += 2;
+        CK(crossgram_launch(h->prog, h->xs, h->d, Mc, Mpad, h->x, h->d, h->N, h->Npad, h->d, h->Kst, h->Npad, h->st));
+        CK(rowdot_launch(h->Kst, h->Npad, h->alpha, Mc, h->Npad, h->pmu, h->st));          // GP.jl:26
+        CK(cudaMemcpyAsync(mu + m0, h->pmu, sizeof(double) * Mc, cudaMemcpyDeviceToHost, h->st));
+        if (need_v) {
+            CK(trsm_rec(h, (int)Mpad, 0, (int)h->Npad));                                   // whiten!, GP.jl:27
+            if (var) {
+                h->launches += 2;
+                CK(kdiag_launch(h->prog, h->xs, h->d, Mc, h->pkdiag, h->st));
+                CK(rowvar_launch(h->Kst, h->Npad, h->pkdiag, Mc, h->Npad, h->pvar, h->st));
+                CK(cudaMemcpyAsync(var + m0, h->pvar, sizeof(double) * Mc, cudaMemcpyDeviceToHost, h->st));
+            }
+            if (cov) {                                                                      // GP.jl:51-54
+                ++h->launches;
+                CK(gram_full_launch(h->prog, h->xs, h->d, Mc, Mpad, h->d, h->Kss, Mpad, h->st));
+                GemmBuf bk{h->tma_ok ? &h->mapKst : nullptr, h->Kst, h->Npad};
+                GemmDesc g = gemm_desc_default();
+                g.A = GemmOperand{bk, bufNone(), 0, 0};
+                g.B = GemmOperand{bk, bufNone(), 0, 0};
+                g.C = h->Kss; g.ldc = Mpad; g.M = (int)Mpad; g.N = (int)Mpad; g.K = (int)h->Npad;
+                g.alpha = -1.0; g.beta = 1.0;
+                CK(launch_gemm(h, g));
+                CK(cudaMemcpy2DAsync(cov, sizeof(double) * M, h->Kss, sizeof(double) * Mpad, sizeof(double) * M, M,
+                                     cudaMemcpyDeviceToHost, h->st));
+            }
+        }
+        CK(cudaStreamSynchronize(h->st));
+    }
+    CK(cudaEventRecord(h->ev3, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->ms[5] = ev_ms(h->ev2, h->ev3);
+    return GPB200_OK;
+}
+
+int gpb200_get_gram(gpb200_handle* h, double* K) {
+    if (!h || !K) return GPB200_EINVAL;
+    if (!h->has_data || !h->has_kernel) return fail(h, GPB200_ESTATE, "get_gram: set_data and set_kernel first");
+    CK(cudaSetDevice(h->device));
+    double* tmp = nullptr;
+    const size_t nn = sizeof(double) * (size_t)h->Npad * (size_t)h->Npad;
+    CK(cudaMalloc(&tmp, nn));
+    cudaError_t e = gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, h->n_noise, h->nugget,
+                                      tmp, h->Npad, h->st);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(K, sizeof(double) * h->N, tmp, sizeof(double) * h->Npad, sizeof(double) * h->N, h->N,
+                              cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    cudaFree(tmp);
+    CK(e);
+    const int64_t N = h->N;
+    for (int64_t i = 0; i < N; ++i)
+        for (int64_t j = i + 1; j < N; ++j) K[i * N + j] = K[j * N + i];
+    return GPB200_OK;
+}
+
+int gpb200_get_factor(gpb200_handle* h, double* U) {
+    if (!h || !U) return GPB200_EINVAL;
+    if (!h->factored) return fail(h, GPB200_ESTATE, "get_factor: factorize first");
+    CK(cudaSetDevice(h->device));
+    const int64_t N = h->N;
+    CK(cudaMemcpy2DAsync(U, sizeof(double) * N, h->F, sizeof(double) * h->ld, sizeof(double) * N, N,
+                         cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    // row-major lower L == column-major upper U; clear the other triangle (scratch on the device)
+    for (int64_t j = 0; j < N; ++j)
+        for (int64_t i = j + 1; i < N; ++i) U[j * N + i] = 0.0;
+    return GPB200_OK;
+}
+
+int gpb200_get_inverse(gpb200_handle* h, double* Kinv) {
+    if (!h || !Kinv) return GPB200_EINVAL;
+    if (!h->inv_ready) return fail(h, GPB200_ESTATE, "get_inverse: grad_prepare first");
+    CK(cudaSetDevice(h->device));
+    const int64_t N = h->N;
+    CK(cudaMemcpy2DAsync(Kinv, sizeof(double) * N, h->G, sizeof(double) * h->ld, sizeof(double) * N, N,
+                         cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (int64_t i = 0; i < N; ++i)
+        for (int64_t j = i + 1; j < N; ++j) Kinv[i * N + j] = Kinv[j * N + i];
+    return GPB200_OK;
+}
+
+int gpb200_dgemm_nt_device(gpb200_handle* h, int impl, int64_t M, int64_t N, int64_t K, double alpha,
+                           const double* dA, int64_t lda, const double* dB, int64_t ldb, double beta, double* dC,
+                           int64_t ldc, int lower_only, int reps, double* ms) {
+    if (!h || !dA || !dB || !dC) return GPB200_EINVAL;
+    if (M % TILE || N % TILE || K % 16 || M <= 0 || N <= 0 || K <= 0 || reps < 1)
+        return fail(h, GPB200_EINVAL, "dgemm_nt: M,N multiples of 128, K multiple of 16");
+    CK(cudaSetDevice(h->device));
+    CUtensorMap ma{}, mb{};
+    const bool tma = gemm_make_tensor_map(&ma, dA, M, K, lda) && gemm_make_tensor_map(&mb, dB, N, K, ldb);
+    if (impl == 0 && !tma) return fail(h, GPB200_ECUDA, "dgemm_nt: TMA descriptors unavailable");
+    GemmDesc g = gemm_desc_default();
+    g.A = GemmOperand{GemmBuf{&ma, dA, lda}, bufNone(), 0, 0};
+    g.B = GemmOperand{GemmBuf{&mb, dB, ldb}, bufNone(), 0, 0};
+    g.C = dC; g.ldc = ldc; g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    g.alpha = alpha; g.beta = beta;
+    g.flags = lower_only ? GEMM_LOWER_ONLY : 0;
+    CK(cudaEventRecord(h->ev0, h->st));
+    for (int r = 0; r < reps; ++r) { ++h->launches; CK(gemm_nt_launch(g, impl, h->st)); }
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (ms) *ms = ev_ms(h->ev0, h->ev1);
+    return GPB200_OK;
+}
+
+int gpb200_nccl_unique_id(char* id128) { (void)id128; return GPB200_ENCCL; }
+int gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128) {
+    (void)nranks; (void)rank; (void)id128;
+    return fail(h, GPB200_ENCCL, "multi-GPU path not built in this revision");
+}
+
+}  // extern "C"

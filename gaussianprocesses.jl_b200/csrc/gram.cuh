@@ -1,0 +1,23 @@
+// gram.cuh -- launchers of the Gram / cross-Gram / gradient-trace kernels (see gram.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kprog.cuh"
+
+// lower tiles of K_y (+ noise on the diagonal, identity in the padding) into G (row-major, ld = ldg)
+cudaError_t gram_lower_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad,
+                              const double* noise_var, int64_t n_noise, double nugget, double* G, int64_t ldg,
+                              cudaStream_t st);
+// Kst[m, n] = k(xs_m, x_n), M_pad x N_pad, zero padding
+cudaError_t crossgram_launch(const KProg& P, const double* xs, int64_t ldxs, int64_t M, int64_t Mpad, const double* x,
+                             int64_t ldx, int64_t N, int64_t Npad, int d, double* Kst, int64_t ldk, cudaStream_t st);
+// Kss[m, m'] = k(xs_m, xs_m'), full M_pad x M_pad
+cudaError_t gram_full_launch(const KProg& P, const double* xs, int64_t ldxs, int64_t M, int64_t Mpad, int d,
+                             double* Kss, int64_t ldk, cudaStream_t st);
+cudaError_t kdiag_launch(const KProg& P, const double* xs, int64_t ldxs, int64_t M, double* out, cudaStream_t st);
+// number of accumulators per tile: n_theta + 1 (last = tr(A))
+int trace_num_acc(const KProg& P);
+// part: [tiles][nacc] scratch; out: [nacc] = {dmll_kernel[0..n_theta), tr(A)}
+cudaError_t trace_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad,
+                         const double* alpha, const double* Kinv, int64_t ldg, double* part, double* out,
+                         cudaStream_t st);

@@ -1,0 +1,7 @@
+// potrf_base.cuh -- 128 x 128 diagonal-tile Cholesky + triangular inverse (see potrf_base.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+// tiles at diagonal offsets p0 + b*tile_stride, b < ntiles.  *info must be initialised to INT_MAX.
+cudaError_t potrf128_launch(const double* G, int64_t ldg, double* F, int64_t ldf, double* Dinv, double* DinvT,
+                            double* logd, int* info, int p0, int ntiles, int tile_stride, cudaStream_t st);

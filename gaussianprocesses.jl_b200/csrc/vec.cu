@@ -1,0 +1,162 @@
+// vec.cu -- bandwidth-bound helpers around the factor.
+//
+//  * trsv_lower_fwd / trsv_lower_bwd : alpha = K_y \ r  == dpotrs with one right-hand side
+//    (/root/reference/src/GPE.jl:208, PDMats `\`).  Blocked by the 128-wide tiles of the factor:
+//    step i multiplies the inverted diagonal tile (Dinv, produced by the Cholesky leaf kernel) and
+//    immediately applies the 128-column panel update to the remaining right-hand side, one launch
+//    per block step (every CTA recomputes the 128-vector y_i instead of waiting on a second kernel).
+//    Out of place: the solution blocks go to a separate vector so that no CTA writes a block other
+//    CTAs of the same launch still read.
+//  * fixed-order reductions (dot, sum) so that mll / logdet are bitwise reproducible.
+//  * predictive mean / variance epilogues (/root/reference/src/GP.jl:26, 51-54, 75).
+#include "vec.cuh"
+#include <math.h>
+
+namespace {
+constexpr int T = 128;
+
+// out[r] = sum_c M[r*ld + c] * v[c]   (128x128 tile, 256 threads, v/out in shared memory)
+__device__ __forceinline__ void tile_matvec(const double* __restrict__ M, long long ld, const double* v, double* out) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const double v0 = v[l], v1 = v[l + 32], v2 = v[l + 64], v3 = v[l + 96];
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = w * 16 + rr;
+        const double* row = M + (long long)r * ld;
+        double s = row[l] * v0 + row[l + 32] * v1 + row[l + 64] * v2 + row[l + 96] * v3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (l == 0) out[r] = s;
+    }
+}
+// out[c] = sum_r M[r*ld + c] * v[r]   (transposed), 256 threads: two row halves combined in smem
+__device__ __forceinline__ void tile_matvec_t(const double* __restrict__ M, long long ld, const double* v, double* out, double* scratch) {
+    const int c = threadIdx.x & 127, h = threadIdx.x >> 7;
+    double s = 0.0;
+#pragma unroll 8
+    for (int r = h * 64; r < h * 64 + 64; ++r) s += M[(long long)r * ld + c] * v[r];
+    if (h == 1) scratch[c] = s;
+    __syncthreads();
+    if (h == 0) out[c] = s + scratch[c];
+}
+
+__global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ F, long long ldf, const double* __restrict__ Dinv,
+                                                      double* __restrict__ r, double* __restrict__ yout, int i) {
+    __shared__ double sr[T], sy[T], so[T];
+    const long long p = (long long)i * T;
+    if (threadIdx.x < T) sr[threadIdx.x] = r[p + threadIdx.x];
+    __syncthreads();
+    tile_matvec(Dinv + p * T, T, sr, sy);
+    __syncthreads();
+    const int b = blockIdx.x;
+    if (b == 0) { if (threadIdx.x < T) yout[p + threadIdx.x] = sy[threadIdx.x]; return; }
+    const long long q = (long long)(i + b) * T;
+    tile_matvec(F + q * ldf + p, ldf, sy, so);
+    __syncthreads();
+    if (threadIdx.x < T) r[q + threadIdx.x] -= so[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ F, long long ldf, const double* __restrict__ DinvT,
+                                                      double* __restrict__ z, double* __restrict__ aout, int i) {
+    __shared__ double sz[T], sa[T], so[T], sc[T];
+    const long long p = (long long)i * T;
+    if (threadIdx.x < T) sz[threadIdx.x] = z[p + threadIdx.x];
+    __syncthreads();
+    tile_matvec(DinvT + p * T, T, sz, sa);         // a_i = W_ii' z_i
+    __syncthreads();
+    const int b = blockIdx.x;
+    if (b == 0) { if (threadIdx.x < T) aout[p + threadIdx.x] = sa[threadIdx.x]; return; }
+    const long long q = (long long)(b - 1) * T;    // column block q < i
+    tile_matvec_t(F + p * ldf + q, ldf, sa, so, sc);   // L[i-block, q-block]' a_i
+    __syncthreads();
+    if (threadIdx.x < T) z[q + threadIdx.x] -= so[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) dot_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, double* __restrict__ out) {
+    __shared__ double s[1024];
+    double v = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) v += a[i] * b[i];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+__global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ a, long long n, double* __restrict__ out) {
+    __shared__ double s[1024];
+    double v = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) v += a[i];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+
+// one CTA (256 threads) per row
+__global__ void __launch_bounds__(256) rowdot_kernel(const double* __restrict__ K, long long ldk, const double* __restrict__ alpha,
+                                                     long long N, double* __restrict__ mu) {
+    __shared__ double s[256];
+    const double* row = K + (long long)blockIdx.x * ldk;
+    double v = 0.0;
+    for (long long n = threadIdx.x; n < N; n += 256) v += row[n] * alpha[n];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) mu[blockIdx.x] = s[0];
+}
+__global__ void __launch_bounds__(256) rowvar_kernel(const double* __restrict__ V, long long ldk, const double* __restrict__ kdiag,
+                                                     long long N, double* __restrict__ var) {
+    __shared__ double s[256];
+    const double* row = V + (long long)blockIdx.x * ldk;
+    double v = 0.0;
+    for (long long n = threadIdx.x; n < N; n += 256) { const double t = row[n]; v += t * t; }
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) var[blockIdx.x] = kdiag[blockIdx.x] - s[0];
+}
+__global__ void exp2x_kernel(const double* __restrict__ ln, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = exp(2.0 * ln[i]);
+}
+}  // namespace
+
+cudaError_t trsv_lower_fwd(const double* F, int64_t ldf, const double* Dinv, double* r, double* y, int64_t Npad,
+                           cudaStream_t st, int64_t* launches) {
+    const int nb = (int)(Npad / T);
+    for (int i = 0; i < nb; ++i) {
+        trsv_fwd_step<<<nb - i, 256, 0, st>>>(F, ldf, Dinv, r, y, i);
+        if (launches) ++*launches;
+    }
+    return cudaGetLastError();
+}
+cudaError_t trsv_lower_bwd(const double* F, int64_t ldf, const double* DinvT, double* z, double* a, int64_t Npad,
+                           cudaStream_t st, int64_t* launches) {
+    const int nb = (int)(Npad / T);
+    for (int i = nb - 1; i >= 0; --i) {
+        trsv_bwd_step<<<i + 1, 256, 0, st>>>(F, ldf, DinvT, z, a, i);
+        if (launches) ++*launches;
+    }
+    return cudaGetLastError();
+}
+cudaError_t dot_launch(const double* a, const double* b, int64_t n, double* out, cudaStream_t st) {
+    dot_kernel<<<1, 1024, 0, st>>>(a, b, n, out);
+    return cudaGetLastError();
+}
+cudaError_t sum_launch(const double* a, int64_t n, double* out, cudaStream_t st) {
+    sum_kernel<<<1, 1024, 0, st>>>(a, n, out);
+    return cudaGetLastError();
+}
+cudaError_t rowdot_launch(const double* Kst, int64_t ldk, const double* alpha, int64_t M, int64_t N, double* mu, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    rowdot_kernel<<<(unsigned)M, 256, 0, st>>>(Kst, ldk, alpha, N, mu);
+    return cudaGetLastError();
+}
+cudaError_t rowvar_launch(const double* Vt, int64_t ldk, const double* kdiag, int64_t M, int64_t N, double* var, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    rowvar_kernel<<<(unsigned)M, 256, 0, st>>>(Vt, ldk, kdiag, N, var);
+    return cudaGetLastError();
+}
+cudaError_t exp2x_launch(const double* ln, int64_t n, double* out, cudaStream_t st) {
+    exp2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ln, n, out);
+    return cudaGetLastError();
+}

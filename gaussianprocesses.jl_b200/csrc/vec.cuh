@@ -1,0 +1,18 @@
+// vec.cuh -- O(N^2) / O(N) kernels: blocked triangular solves with one right-hand side,
+// deterministic reductions, predictive mean / variance epilogues (see vec.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+// y = L^-1 r (r is destroyed, y receives the result; length Npad), L lower in F (row-major), Dinv = inverted diagonal tiles
+cudaError_t trsv_lower_fwd(const double* F, int64_t ldf, const double* Dinv, double* r, double* y, int64_t Npad, cudaStream_t st, int64_t* launches);
+// a = L^-T z (z is destroyed, a receives the result)
+cudaError_t trsv_lower_bwd(const double* F, int64_t ldf, const double* DinvT, double* z, double* a, int64_t Npad, cudaStream_t st, int64_t* launches);
+// out[0] = sum_i a[i]*b[i] (b may equal a); fixed-order tree, one CTA
+cudaError_t dot_launch(const double* a, const double* b, int64_t n, double* out, cudaStream_t st);
+cudaError_t sum_launch(const double* a, int64_t n, double* out, cudaStream_t st);
+// mu[m] = sum_n Kst[m,n] alpha[n]
+cudaError_t rowdot_launch(const double* Kst, int64_t ldk, const double* alpha, int64_t M, int64_t N, double* mu, cudaStream_t st);
+// var[m] = kdiag[m] - sum_n Vt[m,n]^2
+cudaError_t rowvar_launch(const double* Vt, int64_t ldk, const double* kdiag, int64_t M, int64_t N, double* var, cudaStream_t st);
+// v[i] = exp(2*ln[i])
+cudaError_t exp2x_launch(const double* ln, int64_t n, double* out, cudaStream_t st);

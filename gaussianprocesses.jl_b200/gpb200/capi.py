@@ -1,0 +1,228 @@
+"""ctypes binding of libgpb200.so -- the same C ABI (include/gpb200.h) the Julia shim `ccall`s.
+
+No CPU fallback: if the shared library is missing or no CUDA device is present, construction of an
+`Engine` raises.  (The library is built in-tree by `__graft_entry__.build()` / `make -C csrc`.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgpb200.so")
+
+OK, EINVAL, ECUDA, ENCCL, ESTATE = 0, -1, -2, -3, -4
+
+# opcodes (include/gpb200.h)
+OP = dict(SE_ISO=1, SE_ARD=2, MAT12_ISO=3, MAT32_ISO=4, MAT52_ISO=5, MAT12_ARD=6, MAT32_ARD=7,
+          MAT52_ARD=8, RQ_ISO=9, RQ_ARD=10, PERIODIC=11, LIN_ISO=12, LIN_ARD=13, POLY=14, NOISE=15,
+          CONST=16, SUM=32, PROD=33)
+MAX_OPS, MAX_THETA, MAX_DIMS, OP_STRIDE = 16, 96, 128, 6
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_H = C.c_void_p
+
+_SIGNATURES = {
+    "gpb200_create": (C.c_int, [C.POINTER(_H), C.c_int]),
+    "gpb200_destroy": (None, [_H]),
+    "gpb200_last_error": (C.c_char_p, [_H]),
+    "gpb200_version": (C.c_int, []),
+    "gpb200_set_data": (C.c_int, [_H, C.c_int64, C.c_int32, _dp, C.c_int64]),
+    "gpb200_set_kernel": (C.c_int, [_H, C.c_int32, _ip, C.c_int32, _ip, C.c_int32]),
+    "gpb200_factorize": (C.c_int, [_H, _dp, _dp, C.c_int64, C.c_double]),
+    "gpb200_logdet": (C.c_int, [_H, _dp]),
+    "gpb200_solve": (C.c_int, [_H, _dp, _dp]),
+    "gpb200_mll": (C.c_int, [_H, _dp, _dp, _dp]),
+    "gpb200_grad_prepare": (C.c_int, [_H]),
+    "gpb200_grad_kernel": (C.c_int, [_H, _dp, _dp, _dp]),
+    "gpb200_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp]),
+    "gpb200_get_gram": (C.c_int, [_H, _dp]),
+    "gpb200_get_factor": (C.c_int, [_H, _dp]),
+    "gpb200_get_inverse": (C.c_int, [_H, _dp]),
+    "gpb200_get_timings": (C.c_int, [_H, _dp, C.c_int32]),
+    "gpb200_launch_count": (C.c_int64, [_H]),
+    "gpb200_set_option": (C.c_int, [_H, C.c_char_p, C.c_int64]),
+    "gpb200_dgemm_nt_device": (C.c_int, [_H, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int64,
+                                         C.c_int, C.c_int, _dp]),
+    "gpb200_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "gpb200_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
+}
+
+_lib = None
+
+
+def declared_symbols():
+    """Every symbol include/gpb200.h declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGNATURES)
+
+
+def load_library():
+    """dlopen libgpb200.so (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libgpb200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C gaussianprocesses.jl_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class PosDefException(np.linalg.LinAlgError):
+    """Mirror of LinearAlgebra.PosDefException(info) thrown by cholesky! (src/GP.jl:110)."""
+
+    def __init__(self, info):
+        super().__init__("matrix is not positive definite; Cholesky factorization failed (leading minor %d)" % info)
+        self.info = info
+
+
+def _as_dp(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Engine:
+    """Owns one gpb200_handle (one GPU).  Thin, 1:1 with the C ABI."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = _H()
+        rc = self._lib.gpb200_create(C.byref(self._h), int(device))
+        if rc != OK:
+            msg = self._lib.gpb200_last_error(None)
+            raise RuntimeError("gpb200_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self.N = 0
+        self.d = 0
+        self.n_theta = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.gpb200_destroy(self._h)
+            self._h = _H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc == OK:
+            return
+        msg = self._lib.gpb200_last_error(self._h)
+        msg = msg.decode() if msg else ""
+        if rc > 0:
+            raise PosDefException(rc)
+        if rc in (EINVAL, ESTATE):
+            raise ValueError("%s: %s" % (what, msg))       # ArgumentError on the Julia side
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
+
+    # -- data / model ---------------------------------------------------------------------
+    def set_data(self, x_pm):
+        """x_pm: (N, d) C-contiguous float64 == Julia's d x N column-major matrix."""
+        x_pm = np.ascontiguousarray(x_pm, dtype=np.float64)
+        N, d = x_pm.shape
+        self._check(self._lib.gpb200_set_data(self._h, N, d, _as_dp(x_pm), d), "set_data")
+        self.N, self.d = N, d
+
+    def set_kernel(self, ops, dims, n_theta):
+        ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, OP_STRIDE)
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        self._check(self._lib.gpb200_set_kernel(self._h, ops.shape[0], ops.ctypes.data_as(_ip), dims.size,
+                                                dims.ctypes.data_as(_ip), int(n_theta)), "set_kernel")
+        self.n_theta = int(n_theta)
+
+    def set_option(self, key, value):
+        self._check(self._lib.gpb200_set_option(self._h, key.encode(), int(value)), "set_option")
+
+    # -- hot path -------------------------------------------------------------------------
+    def factorize(self, theta, log_noise, extra_nugget=0.0):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        ln = np.ascontiguousarray(np.atleast_1d(log_noise), dtype=np.float64)
+        self._check(self._lib.gpb200_factorize(self._h, _as_dp(theta), _as_dp(ln), ln.size, float(extra_nugget)),
+                    "factorize")
+
+    def logdet(self):
+        out = C.c_double()
+        self._check(self._lib.gpb200_logdet(self._h, C.byref(out)), "logdet")
+        return out.value
+
+    def solve(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        if rhs.shape != (self.N,):
+            raise ValueError("solve: rhs must have length N")
+        out = np.empty(self.N)
+        self._check(self._lib.gpb200_solve(self._h, _as_dp(rhs), _as_dp(out)), "solve")
+        return out
+
+    def mll(self, y_minus_mean):
+        r = np.ascontiguousarray(y_minus_mean, dtype=np.float64)
+        if r.shape != (self.N,):
+            raise ValueError("mll: y must have length N")
+        alpha = np.empty(self.N)
+        out = C.c_double()
+        self._check(self._lib.gpb200_mll(self._h, _as_dp(r), _as_dp(alpha), C.byref(out)), "mll")
+        return alpha, out.value
+
+    def grad_prepare(self):
+        self._check(self._lib.gpb200_grad_prepare(self._h), "grad_prepare")
+
+    def grad_kernel(self, alpha=None):
+        g = np.empty(max(self.n_theta, 1))
+        tr = C.c_double()
+        ap = _as_dp(np.ascontiguousarray(alpha, dtype=np.float64)) if alpha is not None else None
+        self._check(self._lib.gpb200_grad_kernel(self._h, ap, _as_dp(g), C.byref(tr)), "grad_kernel")
+        return g[:self.n_theta].copy(), tr.value
+
+    def predict(self, xs_pm, alpha=None, want_var=True, full_cov=False):
+        xs_pm = np.ascontiguousarray(xs_pm, dtype=np.float64)
+        M, d = xs_pm.shape
+        if d != self.d:
+            raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
+        mu = np.empty(M)
+        var = np.empty(M) if want_var else None
+        cov = np.empty((M, M)) if full_cov else None
+        ap = _as_dp(np.ascontiguousarray(alpha, dtype=np.float64)) if alpha is not None else None
+        self._check(self._lib.gpb200_predict(self._h, M, _as_dp(xs_pm), d, ap, _as_dp(mu),
+                                             _as_dp(var) if want_var else None,
+                                             _as_dp(cov) if full_cov else None), "predict")
+        return mu, var, cov
+
+    # -- debug ----------------------------------------------------------------------------
+    def gram(self):
+        K = np.empty((self.N, self.N))
+        self._check(self._lib.gpb200_get_gram(self._h, _as_dp(K)), "get_gram")
+        return K
+
+    def factor_upper(self):
+        """U (upper) with K_y = U'U, as a numpy (N, N) array (row i, col j -> U[i, j])."""
+        buf = np.empty((self.N, self.N))
+        self._check(self._lib.gpb200_get_factor(self._h, _as_dp(buf)), "get_factor")
+        return buf.T.copy()      # buffer is column-major U == row-major L
+
+    def inverse(self):
+        K = np.empty((self.N, self.N))
+        self._check(self._lib.gpb200_get_inverse(self._h, _as_dp(K)), "get_inverse")
+        return K
+
+    def timings(self):
+        ms = np.zeros(8)
+        self._check(self._lib.gpb200_get_timings(self._h, _as_dp(ms), 8), "get_timings")
+        return dict(gram=ms[0], cholesky=ms[1], solve_mll=ms[2], inverse=ms[3], trace=ms[4], predict=ms[5])
+
+    def launch_count(self):
+        return int(self._lib.gpb200_launch_count(self._h))
+
+    def dgemm_nt_device(self, impl, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, lower_only=False, reps=1):
+        ms = C.c_double()
+        self._check(self._lib.gpb200_dgemm_nt_device(self._h, int(impl), M, N, K, float(alpha), C.c_void_p(dA), lda,
+                                                     C.c_void_p(dB), ldb, float(beta), C.c_void_p(dC), ldc,
+                                                     1 if lower_only else 0, int(reps), C.byref(ms)), "dgemm_nt")
+        return ms.value

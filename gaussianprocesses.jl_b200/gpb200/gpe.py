@@ -1,0 +1,204 @@
+"""GPE -- host-side mirror of the reference's exact GP object (src/GPE.jl:3-567) driving the
+B200 engine through the C ABI.  Same field names (x, y, mean, kernel, logNoise, dim, nobs, alpha,
+mll, target, dmll, dtarget), same method names minus Julia's `!`, same gradient order
+[noise; mean; kernel] (src/GPE.jl:298-324) and the same error behaviour (PosDefException /
+ValueError where the reference throws PosDefException / ArgumentError).
+
+This is the Python twin of julia/GPB200.jl's `B200Covariance <: CovarianceStrategy` methods: each
+call below is one of the shim's overloads (update_cK!, \\, logdet, precompute!, dmll_kern!,
+dmll_noise, predictMVN, predict_f).  x follows the reference layout: shape (dim, nobs), one
+observation per column."""
+import math
+
+import numpy as np
+
+from . import capi
+from .kernels import Kernel, flatten
+from .means import Mean, MeanZero
+
+
+def _as_dxn(x):
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:                       # GPE(x::AbstractVector, ...) = GPE(x', ...)  (src/GPE.jl:96-97)
+        x = x[None, :]
+    if x.ndim != 2:
+        raise ValueError("x must be a dim x nobs matrix")
+    return x
+
+
+class GPE:
+    def __init__(self, x, y, mean=None, kernel=None, logNoise=-2.0, device=0, engine=None):
+        if kernel is None or not isinstance(kernel, Kernel):
+            raise ValueError("GPE needs a kernel")
+        self.mean = mean if mean is not None else MeanZero()
+        if not isinstance(self.mean, Mean):
+            raise ValueError("mean must be a Mean")
+        self.kernel = kernel
+        self.logNoise = float(logNoise) if np.ndim(logNoise) == 0 else np.asarray(logNoise, dtype=np.float64).copy()
+        self._eng = engine if engine is not None else capi.Engine(device)
+        self.alpha = None
+        self.mll = float("nan")
+        self.target = float("nan")
+        self.dmll = None
+        self.dtarget = None
+        self._factored_key = None
+        self.fit(x, y)
+
+    # ---- data ----------------------------------------------------------------------------
+    def fit(self, x, y):
+        """fit!(gp, x, y) (src/GPE.jl:128-136): replace the data, rebuild the device state."""
+        x = _as_dxn(x)
+        y = np.asarray(y, dtype=np.float64).ravel()
+        if x.shape[1] != y.size:
+            raise ValueError("Input and output observations must have consistent dimensions.")   # GPE.jl:41
+        self.x, self.y = x, y
+        self.dim, self.nobs = x.shape
+        self._xpm = np.ascontiguousarray(x.T)            # (nobs, dim): Julia's memory layout
+        self._eng.set_data(self._xpm)
+        self._sync_kernel()
+        self.initialise_target()
+        return self
+
+    def _sync_kernel(self):
+        ops, dims, theta, exposed = flatten(self.kernel, self.dim)
+        self._exposed = exposed
+        self._eng.set_kernel(ops, dims, theta.size)
+        self._factored_key = None
+
+    def _theta_full(self):
+        return flatten(self.kernel, self.dim)[2]
+
+    # ---- log target ----------------------------------------------------------------------
+    def noise_variance(self):                             # GPE.jl:269-271
+        return np.exp(2.0 * np.asarray(self.logNoise)) if np.ndim(self.logNoise) else math.exp(2.0 * self.logNoise)
+
+    def update_cK(self):
+        """update_cK!(gp) (src/GPE.jl:169-195): Gram + noise + Cholesky on the device."""
+        self._eng.factorize(self._theta_full(), self.logNoise)
+
+    def update_mll(self, noise=True, domean=True, kern=True):
+        """update_mll!(gp) (src/GPE.jl:202-212)."""
+        if kern or noise:
+            self.update_cK()
+        mu = self.mean.mean(self._xpm)
+        self.alpha, self.mll = self._eng.mll(self.y - mu)
+        return self
+
+    def update_dmll(self, noise=True, domean=True, kern=True):
+        """update_dmll!(gp, precomp) (src/GPE.jl:298-324)."""
+        self._eng.grad_prepare()                                  # precompute! -> get_ααinvcKI!
+        gk_full, trA = self._eng.grad_kernel()                    # dmll_kern! + tr(A)
+        out = []
+        if noise:
+            if np.ndim(self.logNoise):
+                raise AssertionError("num_params(gp.logNoise) == 1")        # GPE.jl:310
+            out.append(math.exp(2.0 * self.logNoise) * trA)        # dmll_noise, GPE.jl:273-275
+        if domean and self.mean.num_params() > 0:
+            out.extend(self.mean.grad_stack(self._xpm).T @ self.alpha)      # dmll_mean!, GPE.jl:282-288
+        if kern:
+            out.extend(gk_full[self._exposed])                     # FixedKernel selection, fixed_kernel.jl:64-66
+        self.dmll = np.array(out, dtype=np.float64)
+        return self
+
+    def update_mll_and_dmll(self, **kw):                           # GPE.jl:332-335
+        self.update_mll(**kw)
+        self.update_dmll(**kw)
+        return self
+
+    def initialise_target(self):                                   # GPE.jl:346-349 (no priors in this mirror)
+        self.update_mll()
+        self.target = self.mll
+        return self
+
+    def update_target(self, **kw):                                 # GPE.jl:356-360
+        self.update_mll(**kw)
+        self.target = self.mll
+        return self
+
+    def update_target_and_dtarget(self, **kw):                     # GPE.jl:387-392
+        self.update_mll_and_dmll(**kw)
+        self.target = self.mll
+        self.dtarget = self.dmll.copy()
+        return self
+
+    # ---- prediction ----------------------------------------------------------------------
+    def predict_f(self, x, full_cov=False):
+        """predict_f(gp, x; full_cov) (src/GP.jl:64-79), batched on the device."""
+        x = _as_dxn(x)
+        if x.shape[0] != self.dim:
+            raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
+        xs = np.ascontiguousarray(x.T)
+        mu, var, cov = self._eng.predict(xs, None, want_var=not full_cov, full_cov=full_cov)
+        mu = mu + self.mean.mean(xs)
+        if full_cov:
+            return mu, cov
+        return mu, np.maximum(var, 0.0)                            # GP.jl:75
+
+    def predict_y(self, x, full_cov=False):                        # GPE.jl:408-416
+        mu, s2 = self.predict_f(x, full_cov=full_cov)
+        nv = self.noise_variance()
+        if full_cov:
+            return mu, s2 + nv * np.eye(s2.shape[0])
+        return mu, s2 + nv
+
+    # ---- parameters ----------------------------------------------------------------------
+    def get_params(self, noise=True, domean=True, kern=True):      # GPE.jl:447-458
+        p = []
+        if noise:
+            p.extend(np.atleast_1d(self.logNoise))
+        if domean:
+            p.extend(self.mean.get_params())
+        if kern:
+            p.extend(self.kernel.get_params())
+        return np.array(p, dtype=np.float64)
+
+    def num_params(self, **kw):
+        return self.get_params(**kw).size
+
+    def set_params(self, hyp, noise=True, domean=True, kern=True):  # GPE.jl:492-510
+        hyp = np.asarray(hyp, dtype=np.float64)
+        i = 0
+        if noise:
+            n = np.size(self.logNoise)
+            self.logNoise = float(hyp[0]) if np.ndim(self.logNoise) == 0 else hyp[:n].copy()
+            i += n
+        if domean:
+            n = self.mean.num_params()
+            self.mean.set_params(hyp[i:i + n])
+            i += n
+        if kern:
+            n = self.kernel.num_params()
+            self.kernel.set_params(list(hyp[i:i + n]))
+            i += n
+        if i != hyp.size:
+            raise ValueError("wrong number of hyper-parameters")
+        return self
+
+    # ---- optimisation (src/optimize.jl:19-97) ----------------------------------------------
+    def optimize(self, noise=True, domean=True, kern=True, maxiter=100, **kw):
+        """optimize!(gp): L-BFGS on -target with the reference's exception filter
+        (PosDefException / ArgumentError -> Inf, parameters rolled back, optimize.jl:46-87)."""
+        from scipy.optimize import minimize
+
+        flags = dict(noise=noise, domean=domean, kern=kern)
+
+        def fg(hyp):
+            prev = self.get_params(**flags)
+            try:
+                if not np.all(np.isfinite(hyp)):
+                    raise ValueError("non-finite hyper-parameter")
+                self.set_params(hyp, **flags)
+                self.update_target_and_dtarget(**flags)
+                return -self.target, -self.dtarget
+            except (np.linalg.LinAlgError, ValueError):
+                self.set_params(prev, **flags)
+                return float("inf"), np.zeros_like(hyp)
+
+        res = minimize(fg, self.get_params(**flags), jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter), **kw)
+        self.set_params(res.x, **flags)
+        self.update_target()
+        return res
+
+
+def GP(x, y, mean, kernel, logNoise=-2.0, **kw):                   # GPE.jl:119
+    return GPE(x, y, mean, kernel, logNoise, **kw)

@@ -1,0 +1,159 @@
+/*
+ * gpb200.h -- C ABI of libgpb200.so: the B200-native exact-GP hot path behind the
+ * GaussianProcesses.jl `CovarianceStrategy` seam.
+ *
+ * There is no FFI in the reference (pure Julia); the boundary this library slots into is the
+ * reference's own strategy-dispatch API (src/GP.jl:10 `abstract type CovarianceStrategy`).  Each
+ * entry point below names the reference method (file:line under /root/reference) it replaces;
+ * INTEGRATION.md shows the Julia `ccall` shim (`B200Covariance <: CovarianceStrategy`) and the
+ * Python ctypes binding that drive exactly these symbols.
+ *
+ * Conventions
+ *   - all matrices FP64.  `x` is Julia's d x N column-major Matrix{Float64} (== N x d row-major,
+ *     one observation per column), passed with its leading dimension `ldx` (>= d).
+ *   - caller owns every host buffer for the duration of the call only; the library owns all
+ *     device memory behind the opaque handle.  Calls are synchronous.
+ *   - return value: 0 OK;  k > 0 = LAPACK-style "leading minor k is not positive definite"
+ *     (shim throws LinearAlgebra.PosDefException(k), cf. src/GP.jl:110, src/optimize.jl:46-61);
+ *     GPB200_EINVAL (<0) invalid argument (-> ArgumentError);  GPB200_ECUDA / GPB200_ENCCL
+ *     runtime failure, message via gpb200_last_error().  A failed factorisation leaves the
+ *     handle reusable with new hyper-parameters.
+ *   - one handle must not be used from two threads at once; distinct handles may be.
+ *   - there is NO CPU fallback: without a CUDA device gpb200_create fails with GPB200_ECUDA.
+ */
+#ifndef GPB200_H
+#define GPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpb200_handle gpb200_handle;
+
+#define GPB200_OK        0
+#define GPB200_EINVAL   (-1)
+#define GPB200_ECUDA    (-2)
+#define GPB200_ENCCL    (-3)
+#define GPB200_ESTATE   (-4)   /* call order violated (e.g. solve before factorize) */
+
+/* ---- kernel program: post-order (RPN) list of ops; 6 int32 per op ------------------------
+ *   {opcode, theta_off, n_theta, dims_off, n_dims, extra}
+ * leaves read theta[theta_off .. theta_off+n_theta) (log-scale, exactly get_params(kernel) order,
+ * src/kernels/pair_kernel.jl:15, src/common.jl:98-104) and the active input dimensions
+ * dims[dims_off .. dims_off+n_dims) (0-based; `Masked`, src/kernels/masked_kernel.jl:23, is
+ * resolved into this list by the shim).  `extra` = polynomial degree for GPB200_OP_POLY.
+ * SUM / PROD pop two values (src/kernels/sum_kernel.jl:15-16, prod_kernel.jl:14-15).
+ * FixedKernel (src/kernels/fixed_kernel.jl:64-69) is resolved in the shim: pass the full
+ * parameter vector of the wrapped kernel, select gradient entries `free` on the host.        */
+#define GPB200_OP_SE_ISO     1   /* src/kernels/se_iso.jl:39-50     theta = [ll, lsigma]          */
+#define GPB200_OP_SE_ARD     2   /* src/kernels/se_ard.jl:43-50     theta = [ll_1..ll_nd, lsigma] */
+#define GPB200_OP_MAT12_ISO  3   /* src/kernels/mat12_iso.jl:41-43                                */
+#define GPB200_OP_MAT32_ISO  4   /* src/kernels/mat32_iso.jl:41-45                                */
+#define GPB200_OP_MAT52_ISO  5   /* src/kernels/mat52_iso.jl:40-44                                */
+#define GPB200_OP_MAT12_ARD  6   /* src/kernels/mat12_ard.jl:43-45, mat.jl:5-18                   */
+#define GPB200_OP_MAT32_ARD  7   /* src/kernels/mat32_ard.jl:43-46                                */
+#define GPB200_OP_MAT52_ARD  8   /* src/kernels/mat52_ard.jl:43-47                                */
+#define GPB200_OP_RQ_ISO     9   /* src/kernels/rq_iso.jl:44-52     theta = [ll, lsigma, lalpha]  */
+#define GPB200_OP_RQ_ARD    10   /* src/kernels/rq_ard.jl:47-54     theta = [ll.., lsigma, lalpha]*/
+#define GPB200_OP_PERIODIC  11   /* src/kernels/periodic.jl:45-51   theta = [ll, lsigma, lp]      */
+#define GPB200_OP_LIN_ISO   12   /* src/kernels/lin_iso.jl:42,71    theta = [ll]                  */
+#define GPB200_OP_LIN_ARD   13   /* src/kernels/lin_ard.jl:69-92    theta = [ll_1..ll_nd]         */
+#define GPB200_OP_POLY      14   /* src/kernels/poly.jl:44,69-70    theta = [lc, lsigma]          */
+#define GPB200_OP_NOISE     15   /* src/kernels/noise.jl:31-52      theta = [lsigma]              */
+#define GPB200_OP_CONST     16   /* src/kernels/const.jl:41         theta = [lsigma]              */
+#define GPB200_OP_SUM       32
+#define GPB200_OP_PROD      33
+
+#define GPB200_MAX_OPS     16
+#define GPB200_MAX_THETA   96
+#define GPB200_MAX_DIMS   128
+#define GPB200_OP_STRIDE    6
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* replaces alloc_cK(covstrat, nobs) (src/GP.jl:14-20): creates the engine on CUDA device
+ * `device`; device buffers are sized at gpb200_set_data.                                   */
+int  gpb200_create(gpb200_handle** out, int device);
+/* Julia finalizer on B200PDMat */
+void gpb200_destroy(gpb200_handle* h);
+/* message of the last failure on this handle (h == NULL: last create failure) */
+const char* gpb200_last_error(gpb200_handle* h);
+int  gpb200_version(void);
+
+/* ---- data + model ---------------------------------------------------------------------- */
+/* GPE ctor / fit! (src/GPE.jl:63-69, 128-136): upload the d x N inputs once; hyper-parameter
+ * independent.  No N x N distance matrix is precomputed (cf. IsotropicData,
+ * src/kernels/stationary.jl:34-40): distances are recomputed from x inside the Gram kernel. */
+int  gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int64_t ldx);
+/* flattened kernel tree (see opcodes above) */
+int  gpb200_set_kernel(gpb200_handle* h, int32_t n_ops, const int32_t* ops,
+                       int32_t n_dims, const int32_t* dims, int32_t n_theta);
+
+/* ---- update_cK! (src/GPE.jl:169-186) + make_posdef! (src/GP.jl:101-112) ------------------
+ * Gram build cov!(...) (src/kernels/kernels.jl:39-50) with K_ii += exp(2*log_noise) (n_noise==1)
+ * or += exp(2*log_noise[i]) (n_noise==N), plus `extra_nugget`, then the Cholesky factorisation.
+ * Returns k>0 if the leading minor k is not positive definite.                              */
+int  gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_noise,
+                      int64_t n_noise, double extra_nugget);
+/* logdet(cK) (src/GPE.jl:210; PDMats: 2*sum(log(diag(U)))) */
+int  gpb200_logdet(gpb200_handle* h, double* logdet);
+/* cK \ rhs (src/GPE.jl:208; PDMats `\` == dpotrs): out = K_y^-1 rhs, both length N on host */
+int  gpb200_solve(gpb200_handle* h, const double* rhs, double* out);
+/* update_mll! body (src/GPE.jl:206-210): alpha = K_y^-1 r, mll = -(r'alpha + logdet + N log 2pi)/2;
+ * alpha stays resident on the device for grad/predict.                                      */
+int  gpb200_mll(gpb200_handle* h, const double* y_minus_mean, double* alpha, double* mll);
+
+/* ---- gradient -------------------------------------------------------------------------- */
+/* precompute!(precomp, gp) -> get_ααinvcKI! (src/GPE.jl:151-164, 262-264): builds K_y^-1 from
+ * the factor (triangular inverse + W'W, N^3*2/3 flop instead of the reference's 2N^3 potrs on
+ * the identity).  The factor is kept: predict after grad needs no refactorisation.           */
+int  gpb200_grad_prepare(gpb200_handle* h);
+/* dmll_kern! (src/GPE.jl:219-241) + dmll_noise's tr(A) (src/GPE.jl:273-275), fused:
+ * dmll_kernel[p] = 1/2 sum_ij A_ij dK_ij/dtheta_p, A = alpha alpha' - K_y^-1;  *trA = tr(A).
+ * `alpha` may be NULL to use the alpha left resident by gpb200_mll.                          */
+int  gpb200_grad_kernel(gpb200_handle* h, const double* alpha, double* dmll_kernel, double* trA);
+
+/* ---- predictMVN / predict_f (src/GP.jl:25-79) ---------------------------------------------
+ * xs: d x M column-major test inputs (leading dim ldxs).  mu_minus_mean[M] = K*' alpha;
+ * var[M] (may be NULL) = k** - |L^-1 k*|^2, NOT clamped (the shim applies max(.,0) as
+ * src/GP.jl:75 does only on the diagonal path); cov[M*M] (may be NULL) = K** - V'V, symmetric.
+ * Batched: one cross-Gram + one blocked triangular solve for all M points (the reference loops
+ * over test points, src/GP.jl:72-76).                                                       */
+int  gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs,
+                    const double* alpha, double* mu_minus_mean, double* var, double* cov);
+
+/* ---- debug / introspection (Base.Matrix(::P), mat(::P), tests) ----------------------------- */
+int  gpb200_get_gram(gpb200_handle* h, double* K);        /* N x N, K_y rebuilt from x, theta   */
+int  gpb200_get_factor(gpb200_handle* h, double* U);      /* N x N column-major upper U, K_y=U'U */
+int  gpb200_get_inverse(gpb200_handle* h, double* Kinv);  /* N x N, after gpb200_grad_prepare    */
+/* per-phase device times (ms) of the last calls:
+ * [0] gram  [1] cholesky  [2] solve+mll  [3] inverse (trtri+lauum)  [4] trace  [5] predict
+ * [6] trailing-update GEMM launches inside [1] (count)  [7] trailing-update GEMM time inside [1] */
+int  gpb200_get_timings(gpb200_handle* h, double* ms, int32_t n);
+/* number of kernel launches issued by this handle since creation */
+int64_t gpb200_launch_count(gpb200_handle* h);
+/* tuning knobs (string key): "nb" outer Cholesky block, "gemm" 0=TMA kernel 1=simple kernel,
+ * "lookahead" 0/1.  Returns GPB200_EINVAL for unknown keys.                                  */
+int  gpb200_set_option(gpb200_handle* h, const char* key, int64_t value);
+
+/* ---- raw kernels exposed for the parity tests and the roofline bench ----------------------
+ * C[M x N] = alpha * A[M x K] * B[N x K]' + beta * C   (all row-major, device pointers,
+ * M,N multiples of 128, K multiple of 16, leading dims multiples of 2); runs the same DMMA
+ * kernel the factorisation uses.  `impl` 0 = TMA/mbarrier kernel, 1 = simple kernel.
+ * Returns the device time of `reps` launches in *ms (reps>=1).                               */
+int  gpb200_dgemm_nt_device(gpb200_handle* h, int impl, int64_t M, int64_t N, int64_t K,
+                            double alpha, const double* dA, int64_t lda,
+                            const double* dB, int64_t ldb, double beta,
+                            double* dC, int64_t ldc, int lower_only, int reps, double* ms);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------- */
+/* rank 0 obtains a 128-byte NCCL unique id, the host side broadcasts it (torch.distributed /
+ * Julia Distributed), every rank then joins.                                                */
+int  gpb200_nccl_unique_id(char* id128);
+int  gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H */

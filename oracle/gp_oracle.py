@@ -1,0 +1,343 @@
+"""CPU oracle for the exact-GP hot path of GaussianProcesses.jl  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy/LAPACK *restatement* of the reference's algorithm (Julia, /root/reference).
+It is the checker for the CUDA path; it is never the thing shipped or measured as the product.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import it.
+
+Parity pin: `tests/test_oracle_golden.py` checks this oracle against the one known-answer
+vector the reference tree holds for this path (perf/benchmarks/simdata.csv + the output recorded
+in perf/benchmarks/notebooks/benchmark_julia.ipynb cell 6), reproduced to 2e-12.
+
+Reference lines restated (paths relative to /root/reference):
+  src/kernels/distance.jl:41-104     direct-difference (weighted) squared Euclidean distances
+  src/kernels/stationary.jl:25-66    cov_ij / dKij_dθ! dispatch through the metric
+  src/kernels/se_iso.jl:39-50 … periodic.jl:45-51 etc.   leaf formulas (see `_LEAVES`)
+  src/kernels/sum_kernel.jl:15-51, prod_kernel.jl:14-68  composite value + product rule
+  src/kernels/masked_kernel.jl:23-63, fixed_kernel.jl:8-69
+  src/GPE.jl:169-186                 update_cK!: K + exp(2 logNoise) I  (scalar or per-point)
+  src/GP.jl:101-112                  make_posdef!: dpotrf('U')
+  src/GPE.jl:202-212                 update_mll!: alpha = K_y \\ (y - mu); mll
+  src/GPE.jl:151-164                 get_ααinvcKI!: potrs on -I, then ger  (A = αα' - K_y^-1)
+  src/GPE.jl:219-241                 dmll_kern!: 1/2 sum_ij A_ij dK_ij/dθ
+  src/GPE.jl:273-324                 dmll_noise / dmll_mean! / gradient order [noise; mean; kernel]
+  src/GP.jl:25-79                    predictMVN!, predict_f (variance clamp at 0)
+
+Kernel "spec" (neutral tuple form shared with the product's host mirror):
+  ("SEIso", [ll, lσ])            ("SEArd", [ll_1..ll_d, lσ])
+  ("Mat12Iso"|"Mat32Iso"|"Mat52Iso", [ll, lσ])     ("Mat12Ard"|..., [ll_1.., lσ])
+  ("RQIso", [ll, lσ, lα])        ("RQArd", [ll_1.., lσ, lα])
+  ("Periodic", [ll, lσ, lp])     ("LinIso", [ll])   ("LinArd", [ll_1..])
+  ("Poly", [lc, lσ], deg)        ("Noise", [lσ])    ("Const", [lσ])
+  ("Sum", left, right)           ("Prod", left, right)
+  ("Masked", inner, [dims 0-based])                 ("Fixed", inner, [free idx 0-based])
+x is stored point-major: shape (N, d)  (== Julia's d×N column-major).
+"""
+import math
+import numpy as np
+
+try:  # LAPACK through scipy's bundled OpenBLAS (the same backend family Julia ships)
+    from scipy.linalg import lapack as _lapack
+except Exception:  # pragma: no cover
+    _lapack = None
+
+LOG2PI = math.log(2.0 * math.pi)
+
+
+# ----------------------------------------------------------------------------------------------
+# distances  (src/kernels/distance.jl:41-104): sum_k (x_ki - x_kj)^2 [* w_k], direct differences
+# ----------------------------------------------------------------------------------------------
+def _sqdist(X1, X2, w=None):
+    n1, d = X1.shape
+    n2 = X2.shape[0]
+    R = np.zeros((n1, n2))
+    for k in range(d):  # same summation order as the reference's @simd loop over k
+        diff = X1[:, k][:, None] - X2[:, k][None, :]
+        if w is None:
+            R += diff * diff
+        else:
+            R += diff * diff * w[k]
+    return R
+
+
+def _sqdist_k(X1, X2, k, wk=1.0):
+    diff = X1[:, k][:, None] - X2[:, k][None, :]
+    return diff * diff * wk
+
+
+def _dot(X1, X2):
+    n1, d = X1.shape
+    S = np.zeros((n1, X2.shape[0]))
+    for k in range(d):
+        S += X1[:, k][:, None] * X2[:, k][None, :]
+    return S
+
+
+# ----------------------------------------------------------------------------------------------
+# leaves: each returns (K, [dK/dθ_p ...])   (gradients only if want_grad)
+# ----------------------------------------------------------------------------------------------
+def _leaf(name, theta, extra, X1, X2, want_grad):
+    th = [float(t) for t in theta]
+    d = X1.shape[1]
+    g = []
+    if name == "SEIso":  # se_iso.jl:39-50
+        l2, s2 = math.exp(2 * th[0]), math.exp(2 * th[1])
+        r = _sqdist(X1, X2)
+        K = s2 * np.exp(-0.5 * r / l2)
+        if want_grad:
+            g = [r / l2 * K, 2.0 * K]
+    elif name == "SEArd":  # se_ard.jl:43-50
+        il2 = np.exp(-2.0 * np.array(th[:-1]))
+        s2 = math.exp(2 * th[-1])
+        assert len(il2) == d, "SEArd: wrong number of length scales"
+        r = _sqdist(X1, X2, il2)
+        K = s2 * np.exp(-r / 2.0)
+        if want_grad:
+            g = [_sqdist_k(X1, X2, p, il2[p]) * K for p in range(d)] + [2.0 * K]
+    elif name in ("Mat12Iso", "Mat32Iso", "Mat52Iso"):  # mat12_iso.jl:41-43, mat32_iso.jl:41-45, mat52_iso.jl:40-44
+        l, s2 = math.exp(th[0]), math.exp(2 * th[1])
+        r = np.sqrt(_sqdist(X1, X2))
+        if name == "Mat12Iso":
+            K = s2 * np.exp(-r / l)
+            dll = r / l * K
+        elif name == "Mat32Iso":
+            s = math.sqrt(3.0) * r / l
+            K = s2 * (1 + s) * np.exp(-s)
+            dll = s2 * s ** 2 * np.exp(-s)
+        else:
+            s = math.sqrt(5.0) * r / l
+            K = s2 * (1 + s + s ** 2 / 3.0) * np.exp(-s)
+            dll = s2 / 3.0 * s ** 2 * (1 + s) * np.exp(-s)
+        if want_grad:
+            dll = np.where(r == 0.0, 0.0, dll)  # mat.jl:24-26
+            g = [dll, 2.0 * K]
+    elif name in ("Mat12Ard", "Mat32Ard", "Mat52Ard"):  # mat12_ard.jl:43-45, mat32_ard.jl:43-46, mat52_ard.jl:43-47
+        il2 = np.exp(-2.0 * np.array(th[:-1]))
+        s2 = math.exp(2 * th[-1])
+        assert len(il2) == d
+        r = np.sqrt(_sqdist(X1, X2, il2))
+        if name == "Mat12Ard":
+            K = s2 * np.exp(-r)
+        elif name == "Mat32Ard":
+            s = math.sqrt(3.0) * r
+            K = s2 * (1 + s) * np.exp(-s)
+        else:
+            s = math.sqrt(5.0) * r
+            K = s2 * (1 + s + s ** 2 / 3.0) * np.exp(-s)
+        if want_grad:
+            for p in range(d):
+                wd = _sqdist_k(X1, X2, p, il2[p])
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    if name == "Mat12Ard":
+                        v = wd / r * K
+                    elif name == "Mat32Ard":
+                        v = 3.0 * s2 * wd * np.exp(-math.sqrt(3.0) * r)
+                    else:
+                        s = math.sqrt(5.0) * r
+                        v = 5.0 / 3.0 * s2 * wd * (1 + s) * np.exp(-s)
+                g.append(np.where(wd > 0, v, 0.0))  # mat.jl:5-18
+            g.append(2.0 * K)
+    elif name == "RQIso":  # rq_iso.jl:44-52
+        l2, s2, al = math.exp(2 * th[0]), math.exp(2 * th[1]), math.exp(th[2])
+        r = _sqdist(X1, X2)
+        K = s2 * (1 + r / (2 * al * l2)) ** (-al)
+        if want_grad:
+            s = r / l2
+            part = 1 + s / (2 * al)
+            g = [s2 * s * part ** (-al - 1), 2.0 * K,
+                 s2 * part ** (-al) * (s / (2 * part) - al * np.log(part))]
+    elif name == "RQArd":  # rq_ard.jl:47-54
+        il2 = np.exp(-2.0 * np.array(th[:-2]))
+        s2, al = math.exp(2 * th[-2]), math.exp(th[-1])
+        assert len(il2) == d
+        r = _sqdist(X1, X2, il2)
+        part = 1 + r / (2 * al)
+        K = s2 * (1 + 0.5 * r / al) ** (-al)
+        if want_grad:
+            g = [s2 * _sqdist_k(X1, X2, p, il2[p]) * part ** (-al - 1) for p in range(d)]
+            g.append(2.0 * K)
+            g.append(s2 * part ** (-al) * (r / (2 * part) - al * np.log(part)))
+    elif name == "Periodic":  # periodic.jl:45-51
+        l2, s2, per = math.exp(2 * th[0]), math.exp(2 * th[1]), math.exp(th[2])
+        r = np.sqrt(_sqdist(X1, X2))
+        K = s2 * np.exp(-2.0 / l2 * np.sin(math.pi * r / per) ** 2)
+        if want_grad:
+            s = 2 * np.sin(math.pi * r / per) ** 2 / l2
+            sp = math.pi * r / per
+            t = 2.0 / l2
+            g = [2 * s2 * s * np.exp(-s), 2.0 * K,
+                 s2 * sp * t * np.sin(2 * sp) * np.exp(-t * np.sin(sp) ** 2)]
+    elif name == "LinIso":  # lin_iso.jl:42,71
+        l2 = math.exp(2 * th[0])
+        K = _dot(X1, X2) / l2
+        if want_grad:
+            g = [-2.0 * K]
+    elif name == "LinArd":  # lin_ard.jl:69-75,92
+        l = np.exp(np.array(th))
+        assert len(l) == d
+        K = np.zeros((X1.shape[0], X2.shape[0]))
+        parts = []
+        for k in range(d):
+            pk = X1[:, k][:, None] * X2[:, k][None, :] * (1.0 / l[k] ** 2)
+            K += pk
+            parts.append(pk)
+        if want_grad:
+            g = [-2.0 * pk for pk in parts]
+    elif name == "Poly":  # poly.jl:44,69-70
+        c, s2, deg = math.exp(th[0]), math.exp(2 * th[1]), int(extra)
+        xy = _dot(X1, X2)
+        K = s2 * (c + xy) ** deg
+        if want_grad:
+            g = [c * deg * s2 * (c + xy) ** (deg - 1), 2.0 * K]
+    elif name == "Noise":  # noise.jl:31-52  (isapprox per coordinate, rtol = sqrt(eps))
+        s2 = math.exp(2 * th[0])
+        rtol = math.sqrt(np.finfo(float).eps)
+        same = np.ones((X1.shape[0], X2.shape[0]), dtype=bool)
+        for k in range(d):
+            a = X1[:, k][:, None]
+            b = X2[:, k][None, :]
+            same &= np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b))
+        K = np.where(same, s2, 0.0)
+        if want_grad:
+            g = [2.0 * K]
+    elif name == "Const":  # const.jl:41
+        s2 = math.exp(2 * th[0])
+        K = np.full((X1.shape[0], X2.shape[0]), s2)
+        if want_grad:
+            g = [2.0 * K]
+    else:
+        raise ValueError("unknown kernel leaf %r" % (name,))
+    return K, g
+
+
+def num_params(spec):
+    name = spec[0]
+    if name in ("Sum", "Prod"):
+        return num_params(spec[1]) + num_params(spec[2])
+    if name == "Masked":
+        return num_params(spec[1])
+    if name == "Fixed":
+        return len(spec[2])
+    return len(spec[1])
+
+
+def cov_and_grads(spec, X1, X2=None, want_grad=False):
+    """K(X1,X2) and the list of dK/dθ_p in get_params order (kernels.jl:31-71, 89-131)."""
+    X1 = np.ascontiguousarray(X1, dtype=np.float64)
+    X2 = X1 if X2 is None else np.ascontiguousarray(X2, dtype=np.float64)
+    name = spec[0]
+    if name in ("Sum", "Prod"):
+        Kl, gl = cov_and_grads(spec[1], X1, X2, want_grad)
+        Kr, gr = cov_and_grads(spec[2], X1, X2, want_grad)
+        if name == "Sum":  # sum_kernel.jl:15-16, 34-51
+            return Kl + Kr, gl + gr
+        return Kl * Kr, [a * Kr for a in gl] + [Kl * b for b in gr]  # prod_kernel.jl:14-15, 39-68
+    if name == "Masked":  # masked_kernel.jl:23,44-63
+        dims = list(spec[2])
+        return cov_and_grads(spec[1], X1[:, dims], X2[:, dims], want_grad)
+    if name == "Fixed":  # fixed_kernel.jl:64-69
+        K, g = cov_and_grads(spec[1], X1, X2, want_grad)
+        return K, [g[f] for f in spec[2]] if want_grad else []
+    extra = spec[2] if len(spec) > 2 else None
+    return _leaf(name, spec[1], extra, X1, X2, want_grad)
+
+
+def cov(spec, X1, X2=None):
+    return cov_and_grads(spec, X1, X2, False)[0]
+
+
+# ----------------------------------------------------------------------------------------------
+# means (host-side in the product too; src/means/*.jl)
+# ----------------------------------------------------------------------------------------------
+def mean_and_grads(mspec, X):
+    """mspec: ("MeanZero",) | ("MeanConst", beta) | ("MeanLin", [beta...]).  Returns mu[N], G[N,nm]."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    if mspec[0] == "MeanZero":
+        return np.zeros(n), np.zeros((n, 0))
+    if mspec[0] == "MeanConst":
+        return np.full(n, float(mspec[1])), np.ones((n, 1))
+    if mspec[0] == "MeanLin":
+        b = np.asarray(mspec[1], dtype=np.float64)
+        return X @ b, X.copy()
+    raise ValueError(mspec)
+
+
+# ----------------------------------------------------------------------------------------------
+# the hot path
+# ----------------------------------------------------------------------------------------------
+def _potrf_upper(Ky):
+    if _lapack is not None:
+        U, info = _lapack.dpotrf(Ky, lower=0, clean=1, overwrite_a=0)
+        if info != 0:
+            raise np.linalg.LinAlgError("PosDefException(%d)" % info)
+        return U
+    return np.linalg.cholesky(Ky).T
+
+
+def _potrs_upper(U, B):
+    if _lapack is not None:
+        X, info = _lapack.dpotrs(U, B, lower=0)
+        assert info == 0
+        return X
+    import scipy.linalg as sl
+    return sl.cho_solve((U, False), B)
+
+
+def gram(spec, X, log_noise, extra_nugget=0.0):
+    """K_y = K + exp(2 logNoise) I (scalar) or + diag(exp(2 logNoise_i)) (GPE.jl:169-186)."""
+    K = cov(spec, X)
+    ln = np.atleast_1d(np.asarray(log_noise, dtype=np.float64))
+    if ln.size == 1:
+        K = K + (math.exp(2 * float(ln[0])) + extra_nugget) * np.eye(X.shape[0])
+    else:
+        K = K + np.diag(np.exp(2 * ln) + extra_nugget)
+    return K
+
+
+def fit(spec, X, y, log_noise, mspec=("MeanZero",), extra_nugget=0.0):
+    """update_mll! (GPE.jl:202-212).  Returns dict(U, alpha, mll, logdet, Ky)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    Ky = gram(spec, X, log_noise, extra_nugget)
+    U = _potrf_upper(Ky)
+    mu, _ = mean_and_grads(mspec, X)
+    r = y - mu
+    alpha = _potrs_upper(U, r)
+    logdet = 2.0 * np.sum(np.log(np.diag(U)))
+    mll = -(r @ alpha + logdet + LOG2PI * X.shape[0]) / 2.0
+    return dict(U=U, alpha=alpha, mll=mll, logdet=logdet, Ky=Ky, resid=r)
+
+
+def mll_and_dmll(spec, X, y, log_noise, mspec=("MeanZero",), extra_nugget=0.0):
+    """update_mll_and_dmll! (GPE.jl:332-335).  dmll order = [noise; mean; kernel] (GPE.jl:298-324)."""
+    f = fit(spec, X, y, log_noise, mspec, extra_nugget)
+    n = X.shape[0]
+    A = _potrs_upper(f["U"], -np.eye(n))            # GPE.jl:157-162  (the reference's 2N^3 form)
+    A += np.outer(f["alpha"], f["alpha"])           # GPE.jl:163  ger!
+    _, grads = cov_and_grads(spec, X, None, True)
+    dk = np.array([0.5 * np.sum(A * G) for G in grads])       # GPE.jl:226-239
+    ln = np.atleast_1d(np.asarray(log_noise, dtype=np.float64))
+    dnoise = math.exp(2 * float(ln[0])) * np.trace(A) if ln.size == 1 else float("nan")  # GPE.jl:273-275
+    _, MG = mean_and_grads(mspec, X)
+    dmean = MG.T @ f["alpha"]                       # GPE.jl:282-288
+    f["dmll"] = np.concatenate([[dnoise], dmean, dk])
+    f["dmll_kernel"] = dk
+    f["trA"] = float(np.trace(A))
+    f["A"] = A
+    return f
+
+
+def predict_f(spec, X, f, Xs, mspec=("MeanZero",), full_cov=False):
+    """predict_f / predictMVN! (GP.jl:25-79).  f = result of fit()."""
+    import scipy.linalg as sl
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+    Kc = cov(spec, X, Xs)                           # N x M   (GP.jl:44)
+    Kp = cov(spec, Xs, Xs)                          # M x M   (GP.jl:45)
+    mx, _ = mean_and_grads(mspec, Xs)
+    mu = mx + Kc.T @ f["alpha"]                     # GP.jl:26
+    V = sl.solve_triangular(f["U"], Kc, trans="T", lower=False)   # whiten!: U^-T Kc  (GP.jl:27)
+    if full_cov:
+        return mu, Kp - V.T @ V                     # GP.jl:51-54
+    var = np.diag(Kp) - np.sum(V * V, axis=0)
+    return mu, np.maximum(var, 0.0)                 # GP.jl:75
