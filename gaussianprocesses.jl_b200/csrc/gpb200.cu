@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -71,8 +72,15 @@ struct gpb200_handle {
     int gemm_impl = 0;
     int lookahead = 0;
     // stats
-    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int64_t launches = 0;
+    bool own_stream = true;
+    // per-launch GEMM profiling (option "profile"): event pairs + executed flops of every GEMM launch
+    int profile = 0;
+    std::vector<cudaEvent_t> pev;
+    size_t pev_used = 0;
+    double gemm_flops_exec = 0.0;
+    int64_t gemm_launches = 0;
     std::string err;
 };
 
@@ -112,9 +120,57 @@ GemmBuf bufDinv(gpb200_handle* h) { return GemmBuf{h->tma_ok ? &h->mapDinv : nul
 GemmBuf bufDinvT(gpb200_handle* h) { return GemmBuf{h->tma_ok ? &h->mapDinvT : nullptr, h->DinvT, TILE}; }
 GemmBuf bufNone() { return GemmBuf{nullptr, nullptr, 0}; }
 
+// flops the GEMM launch executes (tile-granular: whole 128x128 tiles, clipped k ranges)
+double gemm_exec_flops(const GemmDesc& d) {
+    double total = 0.0;
+    for (int z = 0; z < d.batch; ++z) {
+        const int zo = z * d.zstep;
+        const int Mz = std::min(d.M, d.m_lim - zo), Nz = std::min(d.N, d.n_lim - zo), Kz = std::min(d.K, d.k_lim - zo);
+        if (Mz <= 0 || Nz <= 0 || Kz <= 0) continue;
+        const int tm = Mz / TILE, tn = Nz / TILE;
+        for (int bm = 0; bm < tm; ++bm) {
+            const int bn_hi = (d.flags & GEMM_LOWER_ONLY) ? bm + 1 : tn;
+            for (int bn = 0; bn < bn_hi; ++bn) {
+                int lo = (d.flags & GEMM_KLO_M) ? bm * TILE : 0;
+                int hi = Kz;
+                if (d.flags & GEMM_KHI_M) hi = std::min(hi, (bm + 1) * TILE);
+                if (d.flags & GEMM_KHI_N) hi = std::min(hi, (bn + 1) * TILE);
+                if (hi > lo) total += 2.0 * TILE * TILE * (double)(hi - lo);
+            }
+        }
+    }
+    return total;
+}
+
 cudaError_t launch_gemm(gpb200_handle* h, const GemmDesc& d) {
     ++h->launches;
-    return gemm_nt_launch(d, h->tma_ok ? h->gemm_impl : 1, h->st);
+    const int impl = h->tma_ok ? h->gemm_impl : 1;
+    if (!h->profile) return gemm_nt_launch(d, impl, h->st);
+    if (h->pev_used + 2 > h->pev.size()) {
+        const size_t old = h->pev.size();
+        h->pev.resize(old + 512);
+        for (size_t i = old; i < h->pev.size(); ++i) cudaEventCreate(&h->pev[i]);
+    }
+    cudaEventRecord(h->pev[h->pev_used++], h->st);
+    cudaError_t e = gemm_nt_launch(d, impl, h->st);
+    cudaEventRecord(h->pev[h->pev_used++], h->st);
+    h->gemm_flops_exec += gemm_exec_flops(d);
+    ++h->gemm_launches;
+    return e;
+}
+
+// after a stream sync: fold the recorded GEMM launch durations into ms[6..8] and reset
+void profile_collect(gpb200_handle* h) {
+    if (!h->profile) return;
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < h->pev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->pev[i], h->pev[i + 1]) == cudaSuccess) tot += ms;
+    }
+    h->ms[6] += (double)h->gemm_launches;
+    h->ms[7] += tot;
+    h->ms[8] += h->gemm_flops_exec;
+    h->pev_used = 0; h->gemm_flops_exec = 0.0; h->gemm_launches = 0;
 }
 
 // ---- pieces of the factorisation --------------------------------------------------------------
@@ -353,7 +409,8 @@ void gpb200_destroy(gpb200_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
-    if (h->st) cudaStreamDestroy(h->st);
+    for (auto e : h->pev) cudaEventDestroy(e);
+    if (h->st && h->own_stream) cudaStreamDestroy(h->st);
     delete h;
 }
 
@@ -366,14 +423,34 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "gemm")) { h->gemm_impl = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "profile")) {
+        h->profile = value ? 1 : 0;
+        h->ms[6] = h->ms[7] = h->ms[8] = 0.0;
+        h->pev_used = 0; h->gemm_flops_exec = 0.0; h->gemm_launches = 0;
+        return GPB200_OK;
+    }
     return fail(h, GPB200_EINVAL, "unknown option");
 }
 
 int64_t gpb200_launch_count(gpb200_handle* h) { return h ? h->launches : 0; }
 
+int gpb200_set_stream(gpb200_handle* h, void* stream) {
+    if (!h) return GPB200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    if (h->own_stream && h->st) cudaStreamDestroy(h->st);
+    if (stream) { h->st = (cudaStream_t)stream; h->own_stream = false; }
+    else {
+        h->st = nullptr;
+        CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return GPB200_OK;
+}
+
 int gpb200_get_timings(gpb200_handle* h, double* ms, int32_t n) {
     if (!h || !ms) return GPB200_EINVAL;
-    for (int i = 0; i < n && i < 8; ++i) ms[i] = h->ms[i];
+    for (int i = 0; i < n && i < 12; ++i) ms[i] = h->ms[i];
     return GPB200_OK;
 }
 
@@ -389,7 +466,7 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
         free_data(h);
         h->N = N; h->Npad = Npad; h->ld = Npad; h->d = d;
         const size_t nn = sizeof(double) * (size_t)Npad * (size_t)Npad;
-        CK(cudaMalloc(&h->x, sizeof(double) * N * d));
+        CK(cudaMalloc(&h->x, sizeof(double) * Npad * d));      // Npad rows: N may grow up to Npad without realloc
         CK(cudaMalloc(&h->F, nn));
         CK(cudaMalloc(&h->G, nn));
         CK(cudaMalloc(&h->Dinv, sizeof(double) * Npad * TILE));
@@ -507,6 +584,7 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
     int info = 0;
     CK(cudaMemcpyAsync(&info, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    profile_collect(h);
     h->ms[0] = ev_ms(h->ev0, h->ev1);
     h->ms[1] = ev_ms(h->ev1, h->ev2);
     if (info != INT_MAX) {
@@ -574,6 +652,7 @@ int gpb200_grad_prepare(gpb200_handle* h) {
     CK(inverse_from_factor(h));
     CK(cudaEventRecord(h->ev1, h->st));
     CK(cudaStreamSynchronize(h->st));
+    profile_collect(h);
     h->ms[3] = ev_ms(h->ev0, h->ev1);
     h->inv_ready = true;
     return GPB200_OK;
@@ -658,6 +737,7 @@ int gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, 
     }
     CK(cudaEventRecord(h->ev3, h->st));
     CK(cudaStreamSynchronize(h->st));
+    profile_collect(h);
     h->ms[5] = ev_ms(h->ev2, h->ev3);
     return GPB200_OK;
 }
@@ -731,6 +811,16 @@ int gpb200_dgemm_nt_device(gpb200_handle* h, int impl, int64_t M, int64_t N, int
     CK(cudaEventRecord(h->ev1, h->st));
     CK(cudaStreamSynchronize(h->st));
     if (ms) *ms = ev_ms(h->ev0, h->ev1);
+    return GPB200_OK;
+}
+
+int gpb200_fp64_peak(gpb200_handle* h, double* tflops_dmma, double* tflops_dfma) {
+    if (!h) return GPB200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    double t[2] = {0, 0};
+    CK(fp64_peak_measure(h->st, t));
+    if (tflops_dmma) *tflops_dmma = t[0];
+    if (tflops_dfma) *tflops_dfma = t[1];
     return GPB200_OK;
 }
 

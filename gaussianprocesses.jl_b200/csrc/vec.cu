@@ -120,6 +120,68 @@ __global__ void exp2x_kernel(const double* __restrict__ ln, long long n, double*
 }
 }  // namespace
 
+// ---- FP64 pipe calibration (roofline denominator): DMMA.8x8x4 / DFMA issue rates from registers ----
+namespace {
+__global__ void dmma_peak_kernel(double* out, int iters) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = i;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+cudaError_t fp64_peak_measure(cudaStream_t st, double* tflops) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int warps = 8, iters = 40000;
+    double* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, sizeof(double) * sms * warps * 32);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best[2] = {1e30f, 1e30f};
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        dmma_peak_kernel<<<sms, warps * 32, 0, st>>>(out, iters);
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best[0]) best[0] = ms;
+        cudaEventRecord(e0, st);
+        dfma_peak_kernel<<<sms, warps * 32, 0, st>>>(out, iters);
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best[1]) best[1] = ms;
+    }
+    tflops[0] = 2.0 * 256 * 16.0 * iters * warps * sms / best[0] * 1e-9;
+    tflops[1] = 2.0 * 32 * 16.0 * iters * warps * sms / best[1] * 1e-9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError();
+}
+
 cudaError_t trsv_lower_fwd(const double* F, int64_t ldf, const double* Dinv, double* r, double* y, int64_t Npad,
                            cudaStream_t st, int64_t* launches) {
     const int nb = (int)(Npad / T);

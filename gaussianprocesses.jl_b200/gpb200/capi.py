@@ -43,6 +43,8 @@ _SIGNATURES = {
     "gpb200_get_timings": (C.c_int, [_H, _dp, C.c_int32]),
     "gpb200_launch_count": (C.c_int64, [_H]),
     "gpb200_set_option": (C.c_int, [_H, C.c_char_p, C.c_int64]),
+    "gpb200_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "gpb200_fp64_peak": (C.c_int, [_H, _dp, _dp]),
     "gpb200_dgemm_nt_device": (C.c_int, [_H, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int64,
                                          C.c_int, C.c_int, _dp]),
@@ -213,9 +215,19 @@ class Engine:
         return K
 
     def timings(self):
-        ms = np.zeros(8)
-        self._check(self._lib.gpb200_get_timings(self._h, _as_dp(ms), 8), "get_timings")
-        return dict(gram=ms[0], cholesky=ms[1], solve_mll=ms[2], inverse=ms[3], trace=ms[4], predict=ms[5])
+        ms = np.zeros(12)
+        self._check(self._lib.gpb200_get_timings(self._h, _as_dp(ms), 12), "get_timings")
+        return dict(gram=ms[0], cholesky=ms[1], solve_mll=ms[2], inverse=ms[3], trace=ms[4], predict=ms[5],
+                    gemm_launches=ms[6], gemm_ms=ms[7], gemm_flops=ms[8])
+
+    def set_stream(self, cuda_stream):
+        """Run on the caller's CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream); 0/None = private."""
+        self._check(self._lib.gpb200_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)), "set_stream")
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self._lib.gpb200_fp64_peak(self._h, C.byref(a), C.byref(b)), "fp64_peak")
+        return dict(dmma_tflops=a.value, dfma_tflops=b.value)
 
     def launch_count(self):
         return int(self._lib.gpb200_launch_count(self._h))

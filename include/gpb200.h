@@ -129,13 +129,22 @@ int  gpb200_get_factor(gpb200_handle* h, double* U);      /* N x N column-major 
 int  gpb200_get_inverse(gpb200_handle* h, double* Kinv);  /* N x N, after gpb200_grad_prepare    */
 /* per-phase device times (ms) of the last calls:
  * [0] gram  [1] cholesky  [2] solve+mll  [3] inverse (trtri+lauum)  [4] trace  [5] predict
- * [6] trailing-update GEMM launches inside [1] (count)  [7] trailing-update GEMM time inside [1] */
+ * with option "profile"=1, accumulated since the option was set:
+ * [6] number of DMMA GEMM launches  [7] sum of their device durations (ms, CUDA events around
+ * every launch)  [8] FP64 flops those launches executed (tile-granular)                       */
 int  gpb200_get_timings(gpb200_handle* h, double* ms, int32_t n);
 /* number of kernel launches issued by this handle since creation */
 int64_t gpb200_launch_count(gpb200_handle* h);
 /* tuning knobs (string key): "nb" outer Cholesky block, "gemm" 0=TMA kernel 1=simple kernel,
- * "lookahead" 0/1.  Returns GPB200_EINVAL for unknown keys.                                  */
+ * "lookahead" 0/1, "profile" 0/1.  Returns GPB200_EINVAL for unknown keys.                    */
 int  gpb200_set_option(gpb200_handle* h, const char* key, int64_t value);
+
+/* run all work of this handle on the caller's CUDA stream (cudaStream_t; NULL = a private
+ * stream again), so that the caller's events bracket it (bench.py: torch.cuda.Event).         */
+int  gpb200_set_stream(gpb200_handle* h, void* cuda_stream);
+/* FP64 roofline denominators measured on this device: DMMA.8x8x4 (mma.sync f64, the FP64 tensor
+ * path on sm_100a) and DFMA issue rates, TFLOP/s.                                             */
+int  gpb200_fp64_peak(gpb200_handle* h, double* tflops_dmma, double* tflops_dfma);
 
 /* ---- raw kernels exposed for the parity tests and the roofline bench ----------------------
  * C[M x N] = alpha * A[M x K] * B[N x K]' + beta * C   (all row-major, device pointers,

@@ -1,0 +1,206 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libgpb200.so), against
+the CPU oracle on identical (x, y, hyper-parameters).
+
+Tolerances (north-star): 1e-10 relative on log-mll, alpha (normwise: max|Δ| / max|alpha|),
+predictive mean and variance; 1e-8 relative on dmll.  All FP64."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+from conftest import make_data, kernel_zoo
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+GTOL = 1e-8
+
+
+def _rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _setup(engine, kernel, X, nb=None, gemm=None):
+    import gpb200
+    engine.set_data(X)
+    ops, dims, theta, exposed = gpb200.flatten(kernel, X.shape[1])
+    engine.set_kernel(ops, dims, theta.size)
+    if nb is not None:
+        engine.set_option("nb", nb)
+    if gemm is not None:
+        engine.set_option("gemm", gemm)
+    return theta, exposed
+
+
+@pytest.mark.parametrize("idx", range(20))
+def test_gram_matches_oracle(engine, idx):
+    """cov! parity (kernels.jl:39-50) incl. noise on the diagonal, N not a multiple of the tile."""
+    d = 3
+    X, y, _ = make_data(300, d, 21)
+    name, k = kernel_zoo(d)[idx]
+    theta, _ = _setup(engine, k, X, nb=512, gemm=0)
+    ln = -0.5
+    try:
+        engine.factorize(theta, ln)
+    except np.linalg.LinAlgError:
+        pass                                    # Gram parity does not need a PD matrix
+    K = engine.gram()
+    Ko = orc.gram(k.spec(), X, ln)
+    assert _rel(K, Ko) < 1e-14, name
+    assert np.array_equal(K, K.T)
+
+
+@pytest.mark.parametrize("idx", range(20))
+def test_mll_grad_predict_match_oracle_kernel_zoo(engine, idx):
+    d = 3
+    X, y, Xs = make_data(300, d, 22, m=37)
+    name, k = kernel_zoo(d)[idx]
+    theta, exposed = _setup(engine, k, X, nb=256, gemm=0)
+    ln = -0.4
+    mspec = ("MeanConst", 0.3)
+    o = orc.mll_and_dmll(k.spec(), X, y, ln, mspec)
+    engine.factorize(theta, ln)
+    alpha, mll = engine.mll(y - 0.3)
+    assert abs(mll - o["mll"]) <= RTOL * abs(o["mll"]), name
+    assert _rel(alpha, o["alpha"]) < RTOL, name
+    assert abs(engine.logdet() - o["logdet"]) <= RTOL * abs(o["logdet"]) + 1e-12
+    U = engine.factor_upper()
+    assert _rel(U, o["U"]) < 1e-11, name
+    engine.grad_prepare()
+    Kinv = engine.inverse()
+    assert _rel(Kinv, np.linalg.inv(o["Ky"])) < 1e-9, name
+    gk, trA = engine.grad_kernel()
+    assert _rel(gk[exposed], o["dmll_kernel"]) < GTOL, (name, gk[exposed], o["dmll_kernel"])
+    assert abs(trA - o["trA"]) <= GTOL * abs(o["trA"]) + 1e-10
+    # predict after grad: the factor must still be valid
+    mu, var, _ = engine.predict(Xs)
+    mo, vo = orc.predict_f(k.spec(), X, o, Xs, ("MeanZero",))
+    assert _rel(mu, mo) < RTOL, name
+    assert np.max(np.abs(var - vo)) <= RTOL * np.max(np.abs(vo)) + 1e-13, name
+    mu2, _, cov = engine.predict(Xs, want_var=False, full_cov=True)
+    _, co = orc.predict_f(k.spec(), X, o, Xs, ("MeanZero",), full_cov=True)
+    assert _rel(cov, co) < 1e-9, name
+    assert np.allclose(cov, cov.T, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,nb", [(128, 512), (129, 128), (640, 128), (640, 256), (1100, 512), (1537, 256), (2500, 1024)])
+@pytest.mark.parametrize("gemm", [0, 1])
+def test_blocking_and_padding(engine, N, nb, gemm):
+    """Every recursion shape of the blocked Cholesky / level-parallel inverse, both GEMM loaders."""
+    import gpb200
+    X, y, Xs = make_data(N, 4, N + nb, m=130)
+    k = gpb200.SEIso(0.4, 0.1)
+    theta, exposed = _setup(engine, k, X, nb=nb, gemm=gemm)
+    ln = -0.6
+    o = orc.mll_and_dmll(k.spec(), X, y, ln)
+    engine.factorize(theta, ln)
+    alpha, mll = engine.mll(y)
+    assert abs(mll - o["mll"]) <= RTOL * abs(o["mll"])
+    assert _rel(alpha, o["alpha"]) < RTOL
+    engine.grad_prepare()
+    gk, trA = engine.grad_kernel()
+    assert _rel(gk, o["dmll_kernel"]) < GTOL
+    assert abs(trA - o["trA"]) <= GTOL * abs(o["trA"])
+    assert _rel(engine.solve(y), o["alpha"]) < RTOL
+    mu, var, _ = engine.predict(Xs)
+    mo, vo = orc.predict_f(k.spec(), X, o, Xs)
+    assert _rel(mu, mo) < RTOL
+    assert np.max(np.abs(var - vo)) <= RTOL * np.max(np.abs(vo)) + 1e-13
+    engine.set_option("gemm", 0)
+    engine.set_option("nb", 512)
+
+
+def test_known_answer_simdata(engine):
+    """The reference's own recorded run (perf/benchmarks/simdata.csv, benchmark_julia.ipynb cell 6)."""
+    import gpb200
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "simdata_kat.npz"))
+    X, Y = np.ascontiguousarray(d["X"]), d["Y"]
+    gp = gpb200.GPE(X.T, Y, gpb200.MeanConst(0.0), gpb200.SEIso(0.0, 0.0), 0.0, engine=engine)
+    gp.update_target_and_dtarget()
+    # current-source semantics (no jitter): SURVEY.md Appendix D2
+    assert abs(gp.mll - (-4536.25646128023)) < 1e-10 * 4536.0
+    ref = np.array([-689.6318902132696, -15.731253155037956, 71.19489031472071, -667.2676571953316])
+    assert np.allclose(gp.dmll, ref, rtol=1e-8)
+    assert abs(np.abs(gp.alpha).sum() - 1344.600310514208) < 1e-7
+    # historical run: +1e-5 jitter reproduces the recorded mll to 1e-10
+    th = np.array([0.0, 0.0])
+    engine.factorize(th, 0.0, extra_nugget=1e-5)
+    _, mll = engine.mll(Y)
+    assert abs(mll - float(d["recorded_mll"])) < 1e-10 * 4536.0
+    # benchmark hyper-parameters + predictions: Appendix D3
+    gp = gpb200.GPE(X.T, Y, gpb200.MeanConst(0.0), gpb200.SEIso(0.3, 0.3), 0.3, engine=engine)
+    gp.update_target_and_dtarget()
+    assert abs(gp.mll - (-4955.488218637778)) < 1e-10 * 4955.0
+    ref3 = np.array([-1182.9616810127793, -3.211171983399545, 479.3101304593023, -740.5804238604128])
+    assert np.allclose(gp.dmll, ref3, rtol=1e-8)
+    mu, s2 = gp.predict_f((X[:4] + 0.1).T)
+    assert np.allclose(mu, [-0.18841532, -0.34876141, 0.16691408, 0.73227626], atol=2e-8)
+    assert np.allclose(s2, [0.75560664, 0.48334666, 0.68344073, 0.6690584], atol=2e-8)
+
+
+def test_not_positive_definite_is_recoverable(engine):
+    """cholesky! throws PosDefException (GP.jl:110); the handle stays usable (optimize.jl:46-61)."""
+    import gpb200
+    X, y, _ = make_data(260, 2, 3)
+    X[200] = X[10]                                   # duplicate point, ~zero noise -> singular K_y
+    X[201] = X[10]
+    k = gpb200.SEIso(1.0, 0.0)
+    theta, _ = _setup(engine, k, X)
+    with pytest.raises(gpb200.PosDefException) as ei:
+        engine.factorize(theta, -30.0)
+    assert 1 <= ei.value.info <= 260
+    with pytest.raises(ValueError):
+        engine.mll(y)                                # state error: not factorised
+    engine.factorize(theta, -1.0)                    # same handle, sane noise
+    o = orc.fit(k.spec(), X, y, -1.0)
+    alpha, mll = engine.mll(y)
+    assert abs(mll - o["mll"]) <= RTOL * abs(o["mll"])
+
+
+def test_heteroscedastic_noise_vector(engine):
+    """logNoise::Vector path of update_cK! (GPE.jl:177-186; test/heteroscedastic.jl)."""
+    import gpb200
+    X, y, _ = make_data(333, 2, 8)
+    ln = -1.0 + 0.5 * np.cos(np.arange(333))
+    k = gpb200.Mat52Iso(0.2, 0.1)
+    theta, _ = _setup(engine, k, X)
+    engine.factorize(theta, ln)
+    o = orc.fit(k.spec(), X, y, ln)
+    alpha, mll = engine.mll(y)
+    assert abs(mll - o["mll"]) <= RTOL * abs(o["mll"])
+    assert _rel(alpha, o["alpha"]) < RTOL
+
+
+def test_gpe_mirror_end_to_end(engine):
+    """GPE mirror: dtarget vs finite differences of target (test/kernels.jl:148-164), interpolation
+    (test/gp.jl:32-38), optimize! increases the target (test/optim.jl)."""
+    import gpb200
+    X, _, _ = make_data(200, 2, 4)
+    y = np.sin(X.sum(axis=1))
+    gp = gpb200.GPE(X.T, y, gpb200.MeanConst(0.1), gpb200.SEIso(0.0, 0.0) + gpb200.fix(gpb200.RQIso(0.3, -1.0, 0.2), "lα"), -2.0,
+                    engine=engine)
+    gp.update_target_and_dtarget()
+    p0 = gp.get_params()
+    assert p0.size == 1 + 1 + 2 + 2 and gp.dtarget.size == p0.size
+    fd = np.zeros_like(p0)
+    for i in range(p0.size):
+        for s in (+1, -1):
+            p = p0.copy(); p[i] += s * 1e-5
+            gp.set_params(p); gp.update_target()
+            fd[i] += s * gp.target
+        fd[i] /= 2e-5
+    gp.set_params(p0); gp.update_target_and_dtarget()
+    assert np.allclose(gp.dtarget, fd, rtol=1e-4, atol=1e-4)
+    t0 = gp.target
+    gp.optimize(maxiter=15)
+    assert gp.target > t0
+    mu, s2 = gp.predict_f(X.T)
+    assert np.max(np.abs(mu - y)) < 0.1
+    _, cov = gp.predict_f(X.T[:, :9], full_cov=True)
+    assert np.allclose(np.diag(cov), s2[:9], atol=1e-8)
+    with pytest.raises(ValueError):
+        gp.predict_f(np.zeros((3, 5)))
+    my, sy = gp.predict_y(X.T[:, :5])
+    assert np.allclose(sy, s2[:5] + gp.noise_variance())
