@@ -59,6 +59,18 @@ class GPE:
         self.initialise_target()
         return self
 
+    def reload_data(self, x, y):
+        """Re-upload (x, y) of unchanged shape to the device without re-evaluating the target
+        (one host->device copy of the inputs; the next update_mll! uses them)."""
+        x = _as_dxn(x)
+        y = np.asarray(y, dtype=np.float64).ravel()
+        if x.shape != (self.dim, self.nobs) or y.size != self.nobs:
+            raise ValueError("reload_data: shape changed; use fit")
+        self.x, self.y = x, y
+        self._xpm = np.ascontiguousarray(x.T)
+        self._eng.set_data(self._xpm)
+        return self
+
     def _sync_kernel(self):
         ops, dims, theta, exposed = flatten(self.kernel, self.dim)
         self._exposed = exposed

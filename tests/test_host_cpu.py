@@ -1,0 +1,152 @@
+"""CPU (-m "not gpu"): the C-ABI library loads and exports every symbol include/gpb200.h declares,
+the host-side mirror (kernel flattening, parameter plumbing, gradient order) behaves like the
+reference's plumbing, the product fails loudly without a GPU, and the CPU-baseline port agrees with
+the numpy oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gpb200
+from gpb200 import capi
+from oracle import gp_oracle as orc
+from conftest import make_data, kernel_zoo, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gpb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gpb200_[a-z0-9_]+)\s*\(", hdr)) - {"gpb200_handle"})
+    assert declared == capi.declared_symbols(), set(declared) ^ set(capi.declared_symbols())
+    lib = gpb200.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gpb200_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA"):
+        gpb200.Engine(0)
+
+
+def test_flatten_programs():
+    d = 4
+    for name, k in kernel_zoo(d):
+        ops, dims, theta, exposed = gpb200.flatten(k, d)
+        assert ops.shape[1] == capi.OP_STRIDE and ops.shape[0] <= capi.MAX_OPS
+        leaves = [o for o in ops if o[0] < 32]
+        assert sum(o[2] for o in leaves) == theta.size
+        assert [theta[i] for i in exposed] == pytest.approx(k.get_params())
+        assert len(exposed) == k.num_params() == orc.num_params(k.spec())
+        # post-order: a combinator's right child is the previous op
+        depth = 0
+        for o in ops:
+            depth += 1 if o[0] < 32 else -1
+            assert depth >= 1
+        assert depth == 1
+
+
+def test_masked_and_fixed_resolution():
+    k = gpb200.Masked(gpb200.SEArd([0.1, 0.2], 0.3), [2, 0]) * gpb200.fix(gpb200.RQIso(0.4, 0.5, 0.6), "lσ")
+    ops, dims, theta, exposed = gpb200.flatten(k, 3)
+    assert list(dims[ops[0][3]:ops[0][3] + ops[0][4]]) == [2, 0]
+    assert list(dims[ops[1][3]:ops[1][3] + ops[1][4]]) == [0, 1, 2]
+    assert exposed == [0, 1, 2, 3, 5]
+    k.set_params([1, 2, 3, 4, 5])
+    assert gpb200.flatten(k, 3)[2].tolist() == [1, 2, 3, 4, 0.5, 5]
+    with pytest.raises(ValueError):
+        gpb200.flatten(gpb200.SEArd([0.1, 0.2], 0.3), 3)        # 2 length scales, 3 dims
+    assert gpb200.fix(gpb200.fix(gpb200.SEIso(0.1, 0.2), "ll"), "lσ").num_params() == 0
+
+
+class OracleEngine:
+    """Stand-in with the Engine interface, backed by the CPU oracle -- TEST ONLY, to exercise the
+    GPE host plumbing without a GPU."""
+
+    def __init__(self):
+        self.n_theta = 0
+
+    def set_data(self, x):
+        self.X = np.array(x); self.N, self.d = x.shape
+
+    def set_kernel(self, ops, dims, n_theta):
+        self.n_theta = n_theta
+
+    def bind(self, gp):
+        self.gp = gp
+
+    def factorize(self, theta, ln, extra_nugget=0.0):
+        self.ln = ln
+
+    def mll(self, r):
+        # unfixed spec: the device always sees the full parameter vector
+        def unfix(s):
+            if s[0] == "Fixed":
+                return unfix(s[1])
+            if s[0] in ("Sum", "Prod"):
+                return (s[0], unfix(s[1]), unfix(s[2]))
+            if s[0] == "Masked":
+                return ("Masked", unfix(s[1]), s[2])
+            return s
+        self.spec = unfix(self.gp.kernel.spec())
+        self.f = orc.mll_and_dmll(self.spec, self.X, r, self.ln)
+        return self.f["alpha"], self.f["mll"]
+
+    def grad_prepare(self):
+        pass
+
+    def grad_kernel(self, alpha=None):
+        return self.f["dmll_kernel"], self.f["trA"]
+
+    def predict(self, xs, alpha=None, want_var=True, full_cov=False):
+        mu, v = orc.predict_f(self.spec, self.X, self.f, xs, full_cov=full_cov)
+        return mu, (None if full_cov else np.diag(orc.cov(self.spec, xs, xs)) - (np.diag(orc.cov(self.spec, xs, xs)) - v)), (v if full_cov else None)
+
+
+def _gp(kernel, mean, ln, X, y):
+    eng = OracleEngine()
+    gp = gpb200.GPE.__new__(gpb200.GPE)
+    eng.bind(gp)
+    gpb200.GPE.__init__(gp, X.T, y, mean, kernel, ln, engine=eng)
+    return gp
+
+
+def test_gpe_plumbing_gradient_order_and_flags():
+    X, y, Xs = make_data(50, 2, 9, m=6)
+    k = gpb200.SEIso(0.1, 0.2) + gpb200.fix(gpb200.RQIso(0.3, -0.5, 0.2), "lσ")
+    gp = _gp(k, gpb200.MeanLin([0.1, -0.2]), -1.0, X, y)
+    gp.update_target_and_dtarget()
+    o = orc.mll_and_dmll(k.spec(), X, y, -1.0, ("MeanLin", [0.1, -0.2]))
+    assert gp.mll == pytest.approx(o["mll"], rel=1e-12)
+    assert gp.dmll.size == 1 + 2 + 4                          # [noise; mean; kernel(free)]  GPE.jl:298-324
+    assert np.allclose(gp.dmll, o["dmll"], rtol=1e-10)
+    assert gp.get_params().tolist() == pytest.approx([-1.0, 0.1, -0.2, 0.1, 0.2, 0.3, 0.2])
+    gp.update_dmll(noise=False, domean=False)
+    assert gp.dmll.size == 4
+    gp.update_dmll(kern=False)
+    assert gp.dmll.size == 3
+    p = gp.get_params(); p[0] = -0.7; p[3] = 0.25
+    gp.set_params(p)
+    assert gp.logNoise == -0.7 and gp.kernel.get_params()[0] == 0.25
+    with pytest.raises(ValueError):
+        gp.set_params(p[:-1])
+    with pytest.raises(ValueError):
+        gp.predict_f(np.zeros((3, 4)))                        # GP.jl:65 ArgumentError
+    with pytest.raises(ValueError):
+        gpb200.GPE(X.T, y[:-1], gpb200.MeanZero(), k, -1.0, engine=OracleEngine())   # GPE.jl:41
+    my, vy = gp.predict_y(Xs.T)
+    mf, vf = gp.predict_f(Xs.T)
+    assert np.allclose(vy, vf + np.exp(2 * gp.logNoise))
+
+
+def test_cpu_baseline_port_matches_oracle():
+    from oracle import cpu_baseline as cb
+    X, y, _ = make_data(400, 8, 2)
+    r = cb.seiso_mll_and_dmll(X, y, 0.3, 0.3, 0.3, 0.0)
+    o = orc.mll_and_dmll(("SEIso", [0.3, 0.3]), X, y, 0.3, ("MeanConst", 0.0))
+    assert abs(r["mll"] - o["mll"]) < 1e-10 * abs(o["mll"])
+    assert np.allclose(r["dmll"], o["dmll"], rtol=1e-9)
+    assert np.allclose(r["alpha"], o["alpha"], rtol=1e-9, atol=1e-12)
