@@ -1,0 +1,188 @@
+# GPB200.jl -- the reference-side binding: a `CovarianceStrategy` whose methods `ccall` libgpb200.so.
+#
+# Drop-in behind GaussianProcesses.jl's own strategy seam (src/GP.jl:10); no edit to the reference's
+# source is needed.  Usage:
+#
+#     using GaussianProcesses, GPB200
+#     gp = GPE(x, y, MeanConst(0.0), SEIso(0.3, 0.3), 0.3, B200Covariance())   # src/GPE.jl:68
+#     optimize!(gp); predict_f(gp, xtest)
+#
+# Julia is not installed in the build image, so this file is the *specification* of the binding a
+# maintainer adds (INTEGRATION.md); the executable twin used by the tests is
+# gaussianprocesses.jl_b200/gpb200/{capi,gpe}.py, which drives the identical C ABI (include/gpb200.h).
+module GPB200
+
+using GaussianProcesses
+using LinearAlgebra
+using PDMats
+import GaussianProcesses: CovarianceStrategy, KernelData, EmptyData, alloc_cK, update_cK!, init_precompute,
+                          precompute!, dmll_kern!, dmll_noise, predictMVN, predict_f, predict_full,
+                          AbstractGradientPrecompute, Kernel, Mean, GPE, get_params, num_params, mean,
+                          SumKernel, ProdKernel, Masked, FixedKernel
+import PDMats: AbstractPDMat, dim
+import Base: \, size, Matrix
+import LinearAlgebra: logdet, tr
+
+const LIB = get(ENV, "GPB200_LIB", "libgpb200.so")
+
+# opcodes of include/gpb200.h
+const OP = Dict(SEIso => 1, SEArd => 2, Mat12Iso => 3, Mat32Iso => 4, Mat52Iso => 5, Mat12Ard => 6, Mat32Ard => 7,
+                Mat52Ard => 8, RQIso => 9, RQArd => 10, Periodic => 11, LinIso => 12, LinArd => 13, Poly => 14,
+                Noise => 15, Const => 16)
+const OP_SUM, OP_PROD = 32, 33
+
+struct B200Covariance <: CovarianceStrategy
+    device::Int
+end
+B200Covariance() = B200Covariance(0)
+
+mutable struct B200PDMat <: AbstractPDMat{Float64}
+    handle::Ptr{Cvoid}
+    n::Int
+    exposed::Vector{Int}          # positions of get_params(kernel) inside the device's full theta
+    function B200PDMat(device::Int, n::Int)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:gpb200_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
+        rc == 0 || error("gpb200_create: ", unsafe_string(ccall((:gpb200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        obj = new(h[], n, Int[])
+        finalizer(o -> ccall((:gpb200_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle), obj)
+        return obj
+    end
+end
+
+struct B200Precompute <: AbstractGradientPrecompute
+    cK::B200PDMat
+end
+
+# error convention of include/gpb200.h -> the exceptions optimize!/mcmc filter (src/optimize.jl:46-87)
+function check(cK::B200PDMat, rc::Integer, what)
+    rc == 0 && return
+    rc > 0 && throw(PosDefException(rc))
+    msg = unsafe_string(ccall((:gpb200_last_error, LIB), Cstring, (Ptr{Cvoid},), cK.handle))
+    (rc == -1 || rc == -4) && throw(ArgumentError("$what: $msg"))
+    error("$what failed ($rc): $msg")
+end
+
+# ---- kernel tree -> post-order program (Masked folded into dims, FixedKernel into `exposed`) ----
+function emit!(ops, dims, theta, k::Kernel, active::Vector{Int})
+    if k isa SumKernel || k isa ProdKernel
+        el = emit!(ops, dims, theta, k.kleft, active)
+        er = emit!(ops, dims, theta, k.kright, active)
+        append!(ops, Int32[k isa SumKernel ? OP_SUM : OP_PROD, 0, 0, 0, 0, 0])
+        return vcat(el, er)
+    elseif k isa Masked
+        return emit!(ops, dims, theta, k.kernel, active[collect(k.active_dims)])
+    elseif k isa FixedKernel
+        e = emit!(ops, dims, theta, k.kernel, active)
+        return e[collect(k.free)]
+    else
+        p = get_params(k)
+        toff, doff = length(theta), length(dims)
+        append!(theta, p); append!(dims, Int32.(active .- 1))
+        extra = k isa Poly ? k.deg : 0
+        append!(ops, Int32[OP[Base.typename(typeof(k)).wrapper], toff, length(p), doff, length(active), extra])
+        return collect(toff+1:toff+length(p))
+    end
+end
+
+function flatten(kernel::Kernel, d::Int)
+    ops, dims, theta = Int32[], Int32[], Float64[]
+    exposed = emit!(ops, dims, theta, kernel, collect(1:d))
+    return ops, dims, theta, exposed
+end
+
+# ---- strategy methods (SURVEY.md §8(b); exemplar src/sparse/subsetofregressors.jl) --------------
+KernelData(k::Kernel, X1::AbstractMatrix, X2::AbstractMatrix, ::B200Covariance) = EmptyData()   # no N x N host cache
+
+alloc_cK(cs::B200Covariance, nobs) = B200PDMat(cs.device, nobs)                                 # src/GP.jl:14-20
+
+size(a::B200PDMat) = (a.n, a.n)
+size(a::B200PDMat, i::Int) = a.n
+dim(a::B200PDMat) = a.n
+
+function update_cK!(cK::B200PDMat, x::AbstractMatrix, kernel::Kernel, logNoise, data::KernelData, ::B200Covariance)
+    X = Matrix{Float64}(x)                       # Adjoint / SubArray / ElasticArray -> dense d x N (gotcha 1)
+    d, n = size(X)
+    check(cK, ccall((:gpb200_set_data, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64), cK.handle, n, d, X, d), "set_data")
+    ops, dims, theta, exposed = flatten(kernel, d)
+    cK.exposed = exposed
+    check(cK, ccall((:gpb200_set_kernel, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32),
+                    cK.handle, length(ops) ÷ 6, ops, length(dims), dims, length(theta)), "set_kernel")
+    ln = Float64.(vcat(logNoise))                # Scalar or VectorParam (src/GPE.jl:169 vs :177)
+    check(cK, ccall((:gpb200_factorize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64),
+                    cK.handle, theta, ln, length(ln), 0.0), "factorize")          # rc > 0 -> PosDefException
+    return cK
+end
+
+function \(cK::B200PDMat, y::AbstractVector)                                      # src/GPE.jl:208
+    out = Vector{Float64}(undef, cK.n)
+    check(cK, ccall((:gpb200_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), cK.handle, Vector{Float64}(y), out), "solve")
+    return out
+end
+
+function logdet(cK::B200PDMat)                                                    # src/GPE.jl:210
+    out = Ref{Float64}(0.0)
+    check(cK, ccall((:gpb200_logdet, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}), cK.handle, out), "logdet")
+    return out[]
+end
+
+function Matrix(cK::B200PDMat)                                                    # debug only
+    K = Matrix{Float64}(undef, cK.n, cK.n)
+    check(cK, ccall((:gpb200_get_gram, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), cK.handle, K), "get_gram")
+    return K
+end
+tr(cK::B200PDMat) = tr(Matrix(cK))
+
+init_precompute(::B200Covariance, X, y, k) = nothing                              # replaced per-gp below
+init_precompute(gp::GPE{X,Y,M,K,CS,D,P}) where {X,Y,M,K,CS<:B200Covariance,D,P} = B200Precompute(gp.cK)
+
+function precompute!(pre::B200Precompute, gp)                                     # src/GPE.jl:262-264
+    check(pre.cK, ccall((:gpb200_grad_prepare, LIB), Cint, (Ptr{Cvoid},), pre.cK.handle), "grad_prepare")
+end
+
+function grad_full(pre::B200Precompute, gp)
+    nfull = maximum(pre.cK.exposed; init=0)
+    g = Vector{Float64}(undef, max(nfull, 1)); trA = Ref{Float64}(0.0)
+    check(pre.cK, ccall((:gpb200_grad_kernel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                        pre.cK.handle, gp.alpha, g, trA), "grad_kernel")
+    return g, trA[]
+end
+
+function dmll_kern!(dmll::AbstractVector, gp, pre::B200Precompute, ::B200Covariance)   # src/GPE.jl:265-267
+    g, _ = grad_full(pre, gp)
+    dmll .= g[pre.cK.exposed]                     # FixedKernel selection (fixed_kernel.jl:64-66)
+    return dmll
+end
+
+function dmll_noise(gp::GPE, pre::B200Precompute, ::B200Covariance)               # src/GPE.jl:273-281
+    _, trA = grad_full(pre, gp)
+    return exp(2 * GaussianProcesses.get_value(gp.logNoise)) * trA
+end
+
+# batched prediction instead of the per-column loop of src/GP.jl:72-76
+function predict_raw(gp::GPE, x::AbstractMatrix, full_cov::Bool)
+    size(x, 1) == gp.dim || throw(ArgumentError("Gaussian Process object and input observations do not have consistent dimensions"))
+    X = Matrix{Float64}(x); M = size(X, 2)
+    mu = Vector{Float64}(undef, M)
+    var = full_cov ? C_NULL : Vector{Float64}(undef, M)
+    cov = full_cov ? Matrix{Float64}(undef, M, M) : C_NULL
+    check(gp.cK, ccall((:gpb200_predict, LIB), Cint,
+                       (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       gp.cK.handle, M, X, size(X, 1), gp.alpha, mu, var, cov), "predict")
+    mu .+= mean(gp.mean, X)
+    return mu, (full_cov ? cov : var)
+end
+
+function predict_f(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractMatrix; full_cov::Bool=false) where {X,Y,M,K,CS<:B200Covariance,D,P}
+    mu, s = predict_raw(gp, x, full_cov)
+    return full_cov ? (mu, s) : (mu, max.(s, 0.0))                                 # src/GP.jl:75
+end
+
+function predictMVN(xpred::AbstractMatrix, xtrain, ytrain, kernel::Kernel, meanf::Mean, alpha,
+                    ::B200Covariance, Ktrain::B200PDMat)                           # src/GP.jl:39-49
+    error("predictMVN(B200Covariance) is reached through predict_f(gp, x); call that instead")
+end
+
+export B200Covariance
+
+end # module
