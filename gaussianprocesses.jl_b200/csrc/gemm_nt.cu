@@ -56,11 +56,19 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
     const int Nz = min(p.N, p.n_lim - t.zoff);
     const int Kz = min(p.K, p.k_lim - t.zoff);
     if (p.flags & GEMM_LOWER_ONLY) {
+        // lower trapezoid of an M x N tile grid (M >= N): rows 0..tn-1 triangular, rows >= tn full
         const int lin = blockIdx.x;
-        int bm = (int)((sqrt(8.0 * (double)lin + 1.0) - 1.0) * 0.5);
-        while (bm * (bm + 1) / 2 > lin) --bm;
-        while ((bm + 1) * (bm + 2) / 2 <= lin) ++bm;
-        t.bm = bm; t.bn = lin - bm * (bm + 1) / 2;
+        const int tn = p.N / BN;
+        const int tri = tn * (tn + 1) / 2;
+        if (lin < tri) {
+            int bm = (int)((sqrt(8.0 * (double)lin + 1.0) - 1.0) * 0.5);
+            while (bm * (bm + 1) / 2 > lin) --bm;
+            while ((bm + 1) * (bm + 2) / 2 <= lin) ++bm;
+            t.bm = bm; t.bn = lin - bm * (bm + 1) / 2;
+        } else {
+            const int r = lin - tri;
+            t.bm = tn + r / tn; t.bn = r - (r / tn) * tn;
+        }
     } else {
         t.bn = blockIdx.x; t.bm = blockIdx.y;
     }
@@ -369,8 +377,8 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     const int tm = d.M / BM, tn = d.N / BN;
     dim3 grid;
     if (d.flags & GEMM_LOWER_ONLY) {
-        if (tm != tn) return cudaErrorInvalidValue;
-        grid = dim3((unsigned)(tm * (tm + 1) / 2), 1, (unsigned)d.batch);
+        if (tm < tn) return cudaErrorInvalidValue;
+        grid = dim3((unsigned)(tn * (tn + 1) / 2 + (tm - tn) * tn), 1, (unsigned)d.batch);
     } else {
         grid = dim3((unsigned)tn, (unsigned)tm, (unsigned)d.batch);
     }

@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 enum : int {
-    GEMM_LOWER_ONLY = 1,   // square output, only tiles bm >= bn; diagonal tiles write i >= j only
+    GEMM_LOWER_ONLY = 1,   // M >= N: only tiles bm >= bn (lower trapezoid); diagonal tiles write i >= j only
     GEMM_KLO_M      = 2,   // k starts at bm*128        (A rows are upper-triangular in the frame)
     GEMM_KHI_M      = 4,   // k ends at (bm+1)*128      (A rows are lower-triangular)
     GEMM_KHI_N      = 8,   // k ends at (bn+1)*128      (B rows are lower-triangular)

@@ -14,12 +14,14 @@
 // test/memory.jl:14-19); this engine keeps two on the device and no distance cache.
 //
 // Every O(N^3) step is the NT DMMA GEMM of gemm_nt.cu:
-//   Cholesky (right-looking, outer block nb): leaf potrf128 (+ tile inverse) -> panel TRSM as a
-//   GEMM against the inverted diagonal block -> trailing SYRK.  The inverse of each nb x nb
-//   diagonal block is assembled on the way by the same merges the full inverse uses.
+//   Cholesky: recursive panel factorisation (chol_panel): leaf = potrf128 (tile factor + tile
+//   inverse in one CTA) + a 128-wide TRSM GEMM through the inverted tile; every internal node is one
+//   Schur-complement GEMM over a lower trapezoid with inner dimension = half the block, so ~98% of
+//   the N^3/3 flops run with K >= 1024.  Option "nb" > 0 switches to a right-looking outer loop over
+//   nb-wide panels (the form the multi-GPU block-column distribution uses).
 //   Inverse: bottom-up *level-parallel* triangular inverse -- at level s every pair of adjacent
 //   s x s diagonal blocks is merged independently, W21 = -W_C (L21 W_A), two batched GEMMs per
-//   level, 2 log2(Npad/nb) launches in total -- then K_y^-1 = W' W in ONE triangular SYRK launch.
+//   level, 2 log2(Npad/128) launches in total -- then K_y^-1 = W' W in ONE triangular SYRK launch.
 //   N^3/3 + 2N^3/3 = N^3 flop per mll+gradient (the reference's potrs on the identity costs 7N^3/3).
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -68,7 +70,7 @@ struct gpb200_handle {
     int64_t xs_cap = 0, Kst_rows = 0, Kss_rows = 0;
     CUtensorMap mapKst{};
     // options
-    int nb = 512;
+    int nb = 0;                 // outer Cholesky block; 0 = fully recursive (one panel)
     int gemm_impl = 0;
     int lookahead = 0;
     // stats
@@ -129,7 +131,7 @@ double gemm_exec_flops(const GemmDesc& d) {
         if (Mz <= 0 || Nz <= 0 || Kz <= 0) continue;
         const int tm = Mz / TILE, tn = Nz / TILE;
         for (int bm = 0; bm < tm; ++bm) {
-            const int bn_hi = (d.flags & GEMM_LOWER_ONLY) ? bm + 1 : tn;
+            const int bn_hi = (d.flags & GEMM_LOWER_ONLY) ? std::min(bm + 1, tn) : tn;
             for (int bn = 0; bn < bn_hi; ++bn) {
                 int lo = (d.flags & GEMM_KLO_M) ? bm * TILE : 0;
                 int hi = Kz;
@@ -175,23 +177,23 @@ void profile_collect(gpb200_handle* h) {
 
 // ---- pieces of the factorisation --------------------------------------------------------------
 
-// F[r0.., p..p+n) = G[r0.., p..p+n) * W(p,n)'     (panel TRSM through the inverted diagonal block)
-cudaError_t panel_trsm(gpb200_handle* h, int r0, int rows, int p, int n) {
+// F[r0.., p..p+128) = G[r0.., p..p+128) * W_pp'   (leaf panel TRSM through the inverted diagonal tile)
+cudaError_t panel_trsm_leaf(gpb200_handle* h, int r0, int rows, int p) {
     GemmDesc g = gemm_desc_default();
     g.A = GemmOperand{bufG(h), bufNone(), r0, p};
-    g.B = GemmOperand{bufG(h), bufDinv(h), p, p};
+    g.B = GemmOperand{bufDinv(h), bufNone(), p, 0};
     g.C = h->F; g.ldc = h->ld; g.c_row0 = r0; g.c_col0 = p;
-    g.M = rows; g.N = n; g.K = n;
-    g.flags = GEMM_KHI_N;
+    g.M = rows; g.N = TILE; g.K = TILE;
     return launch_gemm(h, g);
 }
-// G[r0.., r0..) -= F[r0.., p..p+n) F[r0.., p..p+n)'   (lower tiles)
-cudaError_t trailing_syrk(gpb200_handle* h, int r0, int rows, int p, int n) {
+// Schur update of the lower trapezoid G[r0.., r0..r0+cols) -= F[r0.., p..p+k) F[r0..r0+cols, p..p+k)'
+// (rows >= cols; cols == rows gives the classical trailing SYRK)
+cudaError_t schur_update(gpb200_handle* h, int r0, int rows, int cols, int p, int k) {
     GemmDesc g = gemm_desc_default();
     g.A = GemmOperand{bufF(h), bufNone(), r0, p};
     g.B = GemmOperand{bufF(h), bufNone(), r0, p};
     g.C = h->G; g.ldc = h->ld; g.c_row0 = r0; g.c_col0 = r0;
-    g.M = rows; g.N = rows; g.K = n;
+    g.M = rows; g.N = cols; g.K = k;
     g.alpha = -1.0; g.beta = 1.0;
     g.flags = GEMM_LOWER_ONLY;
     return launch_gemm(h, g);
@@ -229,43 +231,49 @@ cudaError_t merge_inverse(gpb200_handle* h, int p, int n1, int n2, int batch) {
     }
 }
 
-// factor the diagonal block [p, p+n) (n <= s, s = 128 * 2^k, p aligned to s) and assemble its inverse
-cudaError_t potrf_block(gpb200_handle* h, int p, int n, int s) {
+// Recursive panel Cholesky: factor columns [p, p+n) for ALL rows below (n <= s, s = 128 * 2^k,
+// p aligned to s).  Every Schur update inside is one NT GEMM whose inner dimension is the half
+// block size, so ~98% of the flops run with K >= 1024 (near-peak DMMA activity); only the
+// 128-wide leaves (tile factorisation + TRSM through the inverted tile) are latency bound.
+cudaError_t chol_panel(gpb200_handle* h, int p, int n, int s) {
+    const int Np = (int)h->Npad;
     cudaError_t e;
     if (s == TILE) {
         ++h->launches;
-        return potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st);
+        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st);
+        if (e != cudaSuccess) return e;
+        const int below = Np - p - TILE;
+        return below > 0 ? panel_trsm_leaf(h, p + TILE, below, p) : cudaSuccess;
     }
     const int hs = s / 2;
-    if (n <= hs) return potrf_block(h, p, n, hs);
-    if ((e = potrf_block(h, p, hs, hs)) != cudaSuccess) return e;
-    const int n2 = n - hs;
-    if ((e = panel_trsm(h, p + hs, n2, p, hs)) != cudaSuccess) return e;
-    if ((e = trailing_syrk(h, p + hs, n2, p, hs)) != cudaSuccess) return e;
-    if ((e = potrf_block(h, p + hs, n2, hs)) != cudaSuccess) return e;
-    return merge_inverse(h, p, hs, n2, 1);
+    if (n <= hs) return chol_panel(h, p, n, hs);
+    if ((e = chol_panel(h, p, hs, hs)) != cudaSuccess) return e;
+    if ((e = schur_update(h, p + hs, Np - p - hs, n - hs, p, hs)) != cudaSuccess) return e;
+    return chol_panel(h, p + hs, n - hs, hs);
 }
 
 cudaError_t cholesky(gpb200_handle* h) {
     const int Np = (int)h->Npad;
+    // outer block: option "nb" (0 = one panel spanning the matrix: fully recursive)
+    int NB = TILE;
+    const int want = h->nb > 0 ? h->nb : Np;
+    while (NB < want && NB < Np) NB *= 2;
     cudaError_t e;
-    for (int p = 0; p < Np; p += h->nb) {
-        const int n = (Np - p < h->nb) ? Np - p : h->nb;
-        if ((e = potrf_block(h, p, n, h->nb)) != cudaSuccess) return e;
+    for (int p = 0; p < Np; p += NB) {
+        const int n = (Np - p < NB) ? Np - p : NB;
+        if ((e = chol_panel(h, p, n, NB)) != cudaSuccess) return e;
         const int rem = Np - p - n;
-        if (rem > 0) {
-            if ((e = panel_trsm(h, p + n, rem, p, n)) != cudaSuccess) return e;
-            if ((e = trailing_syrk(h, p + n, rem, p, n)) != cudaSuccess) return e;
-        }
+        if (rem > 0 && (e = schur_update(h, p + n, rem, rem, p, n)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-// remaining levels of the triangular inverse (blocks of size nb are already inverted), then W'W
+// K_y^-1 from the factor: level-parallel triangular inverse (all pairs of adjacent s x s diagonal
+// blocks merged at once, s = 128, 256, ...: 2 batched GEMM launches per level), then W'W.
 cudaError_t inverse_from_factor(gpb200_handle* h) {
     const int Np = (int)h->Npad;
     cudaError_t e;
-    for (long long s = h->nb; s < Np; s *= 2) {
+    for (long long s = TILE; s < Np; s *= 2) {
         const int batch = (int)((Np + 2 * s - 1) / (2 * s));
         const int n2 = (int)((Np - s < s) ? Np - s : s);
         if ((e = merge_inverse(h, 0, (int)s, n2, batch)) != cudaSuccess) return e;
@@ -395,7 +403,7 @@ int gpb200_create(gpb200_handle** out, int device) {
     const char* env = getenv("GPB200_GEMM");
     if (env) h->gemm_impl = atoi(env);
     env = getenv("GPB200_NB");
-    if (env) { int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048) h->nb = v; }
+    if (env) { int v = atoi(env); if (v == 0 || v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096) h->nb = v; }
     *out = h;
     return GPB200_OK;
 }
@@ -417,8 +425,8 @@ void gpb200_destroy(gpb200_handle* h) {
 int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
     if (!h || !key) return GPB200_EINVAL;
     if (!strcmp(key, "nb")) {
-        if (value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048)
-            return fail(h, GPB200_EINVAL, "nb must be 128, 256, 512, 1024 or 2048");
+        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048 && value != 4096)
+            return fail(h, GPB200_EINVAL, "nb must be 0 (fully recursive) or 128 * 2^k <= 4096");
         h->nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
     if (!strcmp(key, "gemm")) { h->gemm_impl = value ? 1 : 0; return GPB200_OK; }

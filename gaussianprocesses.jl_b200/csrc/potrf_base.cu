@@ -65,22 +65,34 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
             if (threadIdx.x == 0) atomicMin(info, p + j + 1);
             d = 1.0;
         }
-        const double invd = 1.0 / d;
-        if (threadIdx.x == 0) { rs[j] = 1.0 / sqrt(d); logd[p + j] = log(d); }
+        const double invd = __drcp_rn(d);
+        if (threadIdx.x == 0) rs[j] = d;          // pivot; turned into 1/sqrt(d) after the loop
+        // column values this lane needs (live chunks only: 32c+31 > j)
+        double cn[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cn[c] = (32 * c + 31 > j) ? S[(l + 32 * c) * LDS + j] : 0.0;
 #pragma unroll
         for (int ia = 0; ia < 8; ++ia) {
-            const int m = w + 16 * ia;
+            const int m = w + 16 * ia;                 // warp-uniform
             if (m > j) {
                 const double lm = S[m * LDS + j] * invd;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int n = l + 32 * c;
-                    if (n > j && n <= m) a[ia][c] -= lm * S[n * LDS + j];
+                    if (32 * c + 31 > j && 32 * c <= m) {      // warp-uniform: chunk has live columns
+                        const int n = l + 32 * c;
+                        if (n > j && n <= m) a[ia][c] -= lm * cn[c];
+                    }
                 }
             }
         }
     }
-    __syncthreads();   // rs[] complete, all columns published
+    __syncthreads();   // pivots + all columns published
+    if (threadIdx.x < T) {
+        const double d = rs[threadIdx.x];
+        logd[p + threadIdx.x] = log(d);
+        rs[threadIdx.x] = 1.0 / sqrt(d);
+    }
+    __syncthreads();
 
     // ---- write L = S .* rs (lower triangle) ----
     for (int idx = threadIdx.x; idx < T * T; idx += NTH) {
@@ -110,16 +122,17 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
             }
         }
         __syncthreads();
+        double wn[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wn[c] = (32 * c <= i && l + 32 * c <= i) ? S[(l + 32 * c) * LDS + i + 1] : 0.0;
 #pragma unroll
         for (int ia = 0; ia < 8; ++ia) {
             const int m = w + 16 * ia;
             if (m > i) {
                 const double lmi = S[m * LDS + i] * rsi;          // L[m][i]
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int n = l + 32 * c;
-                    if (n <= i) a[ia][c] -= lmi * S[n * LDS + i + 1];
-                }
+                for (int c = 0; c < 4; ++c)
+                    if (32 * c <= i) a[ia][c] -= lmi * wn[c];     // wn == 0 for n > i
             }
         }
     }

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "gaussianprocesses.jl_b200"))
 import gpb200
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-nb = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+nb = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 gemm = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 d = 8
 rng = np.random.default_rng(1)

@@ -40,7 +40,7 @@ def test_gram_matches_oracle(engine, idx):
     d = 3
     X, y, _ = make_data(300, d, 21)
     name, k = kernel_zoo(d)[idx]
-    theta, _ = _setup(engine, k, X, nb=512, gemm=0)
+    theta, _ = _setup(engine, k, X, nb=0, gemm=0)
     ln = -0.5
     try:
         engine.factorize(theta, ln)
@@ -85,7 +85,7 @@ def test_mll_grad_predict_match_oracle_kernel_zoo(engine, idx):
     assert np.allclose(cov, cov.T, rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("N,nb", [(128, 512), (129, 128), (640, 128), (640, 256), (1100, 512), (1537, 256), (2500, 1024)])
+@pytest.mark.parametrize("N,nb", [(128, 512), (129, 128), (640, 128), (640, 256), (1100, 512), (1537, 256), (2500, 1024), (1100, 0), (2500, 0), (3000, 2048)])
 @pytest.mark.parametrize("gemm", [0, 1])
 def test_blocking_and_padding(engine, N, nb, gemm):
     """Every recursion shape of the blocked Cholesky / level-parallel inverse, both GEMM loaders."""
@@ -109,7 +109,7 @@ def test_blocking_and_padding(engine, N, nb, gemm):
     assert _rel(mu, mo) < RTOL
     assert np.max(np.abs(var - vo)) <= RTOL * np.max(np.abs(vo)) + 1e-13
     engine.set_option("gemm", 0)
-    engine.set_option("nb", 512)
+    engine.set_option("nb", 0)
 
 
 def test_known_answer_simdata(engine):
