@@ -25,7 +25,9 @@
 //   N^3/3 + 2N^3/3 = N^3 flop per mll+gradient (the reference's potrs on the identity costs 7N^3/3).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <limits.h>
+#include <nccl.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -83,10 +85,52 @@ struct gpb200_handle {
     size_t pev_used = 0;
     double gemm_flops_exec = 0.0;
     int64_t gemm_launches = 0;
+    // multi-GPU (one process per GPU): replicated F/G, block-column ownership, NCCL over NVLink
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    cudaStream_t st_comm = nullptr;
+    int dist_nb = 1024;                        // width of an owned block column
+    double* pack[2] = {nullptr, nullptr};      // panel staging (double buffered)
+    size_t pack_elems = 0;
+    cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_bcast[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr};
+    cudaEvent_t ev_x = nullptr, ev_y = nullptr;
+    double *ag_send = nullptr, *ag_recv = nullptr;
+    size_t ag_send_elems = 0, ag_recv_elems = 0;
     std::string err;
 };
 
 namespace {
+
+// ---- NCCL, bound at run time (dlopen) so that single-GPU use has no NCCL dependency -------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+} g_nccl;
+
+bool nccl_load() {
+    if (g_nccl.ok) return true;
+    if (!g_nccl.lib) g_nccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.lib) g_nccl.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.lib) return false;
+    void* L = g_nccl.lib;
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(L, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(L, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(L, "ncclCommDestroy");
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(L, "ncclBroadcast");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(L, "ncclAllGather");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(L, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(L, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.Broadcast &&
+                g_nccl.AllGather && g_nccl.AllReduce && g_nccl.GetErrorString;
+    return g_nccl.ok;
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -101,6 +145,18 @@ namespace {
         }                                                                                          \
     } while (0)
 
+#define CKN(call)                                                                                  \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,       \
+                     g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error");            \
+            h->err = buf_;                                                                         \
+            return GPB200_ENCCL;                                                                   \
+        }                                                                                          \
+    } while (0)
+
 int fail(gpb200_handle* h, int code, const char* msg) {
     if (h) h->err = msg;
     return code;
@@ -112,6 +168,10 @@ void free_data(gpb200_handle* h) {
                        &h->pmu, &h->pvar, &h->pkdiag};
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
+    for (int i = 0; i < 2; ++i) { if (h->pack[i]) cudaFree(h->pack[i]); h->pack[i] = nullptr; }
+    if (h->ag_send) cudaFree(h->ag_send);
+    if (h->ag_recv) cudaFree(h->ag_recv);
+    h->ag_send = h->ag_recv = nullptr; h->pack_elems = h->ag_send_elems = h->ag_recv_elems = 0;
     h->xs_cap = h->Kst_rows = h->Kss_rows = 0;
     h->has_data = h->factored = h->inv_ready = h->alpha_ready = false;
 }
@@ -287,6 +347,222 @@ cudaError_t inverse_from_factor(gpb200_handle* h) {
     return launch_gemm(h, g);
 }
 
+
+// ================================================================================================
+// multi-GPU schedules (nranks > 1).  Storage is replicated (every rank holds full F, G, Dinv);
+// WORK is partitioned:
+//   Gram / Cholesky : 1-D block-cyclic ownership of dist_nb-wide block columns.  The owner factors
+//                     its panel (chol_panel), the panel is broadcast (NCCL over NVLink, on a side
+//                     stream, double-buffered), every rank applies it to the block columns it owns.
+//                     The owner of the NEXT panel updates and factors that panel first and ships it
+//                     before finishing its remaining updates (look-ahead), so the broadcast and the
+//                     latency-bound panel factorisation hide behind the other ranks' updates.
+//   inverse         : small levels of the level-parallel triangular inverse are recomputed on every
+//                     rank; from block size 128*nranks upwards each merge is split by column slices
+//                     of W21 (no exchange between its two GEMMs), then all-gathered.
+//   W'W + trace     : tile rows dealt round-robin; only the P+1 partial sums are all-reduced, K^-1
+//                     itself is never exchanged.
+// ================================================================================================
+__global__ void pack_slices_kernel(const double* __restrict__ G, long long ld, double* __restrict__ out,
+                                   int s, int wr, int off, int Np) {
+    const int z = blockIdx.z;
+    const int p = z * 2 * s;
+    const int n2 = min(s, Np - p - s);
+    const int i = blockIdx.y * 32 + threadIdx.y, j = blockIdx.x * 32 + threadIdx.x;
+    if (n2 <= 0 || i >= n2 || j >= wr) return;
+    out[(long long)z * s * wr + (long long)i * wr + j] = G[(long long)(p + s + i) * ld + p + off + j];
+}
+// scatter the gathered W21 column slices of all other ranks into G (lower block) and, transposed, into
+// G's strict-upper block
+__global__ void unpack_slices_kernel(double* __restrict__ G, long long ld, const double* __restrict__ in,
+                                     long long per_rank, int s, int wr, int Np, int nranks, int self) {
+    __shared__ double tile[32][33];
+    const int z = blockIdx.z % ((Np + 2 * s - 1) / (2 * s));
+    const int q = blockIdx.z / ((Np + 2 * s - 1) / (2 * s));
+    if (q == self) return;
+    const int p = z * 2 * s;
+    const int n2 = min(s, Np - p - s);
+    if (n2 <= 0) return;
+    const double* src = in + (long long)q * per_rank + (long long)z * s * wr;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    if (i0 >= n2 || j0 >= wr) return;
+    const int i = i0 + threadIdx.y, j = j0 + threadIdx.x;
+    double v = 0.0;
+    if (i < n2 && j < wr) {
+        v = src[(long long)i * wr + j];
+        G[(long long)(p + s + i) * ld + p + q * wr + j] = v;
+    }
+    tile[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    const int ti = i0 + threadIdx.x, tj = j0 + threadIdx.y;          // transposed: row = column slice index
+    if (ti < n2 && tj < wr) G[(long long)(p + q * wr + tj) * ld + p + s + ti] = tile[threadIdx.x][threadIdx.y];
+}
+
+int dist_alloc(gpb200_handle* h) {
+    const size_t Np = (size_t)h->Npad;
+    const size_t need_pack = Np * (size_t)h->dist_nb + 2 * (size_t)h->dist_nb * TILE + (size_t)h->dist_nb + 16;
+    if (need_pack > h->pack_elems) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->pack[i]) cudaFree(h->pack[i]);
+            h->pack[i] = nullptr;
+            CK(cudaMalloc(&h->pack[i], sizeof(double) * need_pack));
+        }
+        h->pack_elems = need_pack;
+    }
+    const size_t need_recv = Np * Np / 4 + Np * TILE;
+    const size_t need_send = need_recv / h->nranks + Np * TILE;
+    if (need_recv > h->ag_recv_elems) {
+        if (h->ag_recv) cudaFree(h->ag_recv);
+        if (h->ag_send) cudaFree(h->ag_send);
+        h->ag_recv = h->ag_send = nullptr;
+        CK(cudaMalloc(&h->ag_recv, sizeof(double) * need_recv));
+        CK(cudaMalloc(&h->ag_send, sizeof(double) * need_send));
+        h->ag_recv_elems = need_recv; h->ag_send_elems = need_send;
+    }
+    return GPB200_OK;
+}
+
+size_t panel_count(gpb200_handle* h, int p, int n) {
+    return (size_t)(h->Npad - p) * n + 2 * (size_t)n * TILE + (size_t)n;
+}
+// F[p.., p..p+n) + Dinv/DinvT rows p..p+n + logd[p..p+n)  <->  contiguous staging buffer
+cudaError_t panel_pack(gpb200_handle* h, int p, int n, double* buf, bool unpack) {
+    const size_t rows = (size_t)(h->Npad - p);
+    double* fpan = h->F + (size_t)p * h->ld + p;
+    cudaError_t e;
+    if (!unpack) e = cudaMemcpy2DAsync(buf, sizeof(double) * n, fpan, sizeof(double) * h->ld, sizeof(double) * n, rows, cudaMemcpyDeviceToDevice, h->st);
+    else         e = cudaMemcpy2DAsync(fpan, sizeof(double) * h->ld, buf, sizeof(double) * n, sizeof(double) * n, rows, cudaMemcpyDeviceToDevice, h->st);
+    if (e != cudaSuccess) return e;
+    double* b1 = buf + rows * n;
+    double* b2 = b1 + (size_t)n * TILE;
+    double* b3 = b2 + (size_t)n * TILE;
+    const size_t tb = sizeof(double) * (size_t)n * TILE;
+    if (!unpack) {
+        if ((e = cudaMemcpyAsync(b1, h->Dinv + (size_t)p * TILE, tb, cudaMemcpyDeviceToDevice, h->st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(b2, h->DinvT + (size_t)p * TILE, tb, cudaMemcpyDeviceToDevice, h->st)) != cudaSuccess) return e;
+        return cudaMemcpyAsync(b3, h->logd + p, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->st);
+    }
+    if ((e = cudaMemcpyAsync(h->Dinv + (size_t)p * TILE, b1, tb, cudaMemcpyDeviceToDevice, h->st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(h->DinvT + (size_t)p * TILE, b2, tb, cudaMemcpyDeviceToDevice, h->st)) != cudaSuccess) return e;
+    return cudaMemcpyAsync(h->logd + p, b3, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->st);
+}
+
+int cholesky_dist(gpb200_handle* h) {
+    const int Np = (int)h->Npad, R = h->nranks, me = h->rank;
+    int NB = TILE;
+    while (NB < h->dist_nb && NB < Np) NB *= 2;
+    const int nblk = (Np + NB - 1) / NB;
+    auto bp = [&](int b) { return b * NB; };
+    auto bn = [&](int b) { return std::min(NB, Np - b * NB); };
+    auto owner = [&](int b) { return b % R; };
+    auto update = [&](int jb, int b) {      // block column jb <- panel b
+        const int r0 = bp(jb);
+        return schur_update(h, r0, Np - r0, bn(jb), bp(b), bn(b));
+    };
+    // panel 0
+    if (owner(0) == me) {
+        CK(chol_panel(h, 0, bn(0), NB));
+        CK(panel_pack(h, 0, bn(0), h->pack[0], false));
+        CK(cudaEventRecord(h->ev_packed[0], h->st));
+        CK(cudaStreamWaitEvent(h->st_comm, h->ev_packed[0], 0));
+    }
+    CKN(g_nccl.Broadcast(h->pack[0], h->pack[0], panel_count(h, 0, bn(0)), ncclDouble, owner(0), h->comm, h->st_comm));
+    CK(cudaEventRecord(h->ev_bcast[0], h->st_comm));
+    for (int b = 0; b < nblk; ++b) {
+        const int cur = b & 1, nxt = cur ^ 1;
+        CK(cudaStreamWaitEvent(h->st, h->ev_bcast[cur], 0));
+        if (owner(b) != me) CK(panel_pack(h, bp(b), bn(b), h->pack[cur], true));
+        CK(cudaEventRecord(h->ev_unpacked[cur], h->st));
+        bool did_next = false;
+        if (b + 1 < nblk) {
+            if (owner(b + 1) == me) {                         // look-ahead: next panel first
+                CK(update(b + 1, b));
+                CK(chol_panel(h, bp(b + 1), bn(b + 1), NB));
+                CK(panel_pack(h, bp(b + 1), bn(b + 1), h->pack[nxt], false));
+                CK(cudaEventRecord(h->ev_packed[nxt], h->st));
+                CK(cudaStreamWaitEvent(h->st_comm, h->ev_packed[nxt], 0));
+                did_next = true;
+            } else if (b >= 1) {
+                CK(cudaStreamWaitEvent(h->st_comm, h->ev_unpacked[nxt], 0));   // staging buffer free again
+            }
+            CKN(g_nccl.Broadcast(h->pack[nxt], h->pack[nxt], panel_count(h, bp(b + 1), bn(b + 1)), ncclDouble,
+                                 owner(b + 1), h->comm, h->st_comm));
+            CK(cudaEventRecord(h->ev_bcast[nxt], h->st_comm));
+        }
+        for (int jb = b + 1 + (did_next ? 1 : 0); jb < nblk; ++jb)
+            if (owner(jb) == me) CK(update(jb, b));
+    }
+    // first failing pivot over all ranks
+    CK(cudaEventRecord(h->ev_x, h->st));
+    CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
+    CKN(g_nccl.AllReduce(h->info_dev, h->info_dev, 1, ncclInt32, ncclMin, h->comm, h->st_comm));
+    CK(cudaEventRecord(h->ev_y, h->st_comm));
+    CK(cudaStreamWaitEvent(h->st, h->ev_y, 0));
+    return GPB200_OK;
+}
+
+int inverse_dist(gpb200_handle* h) {
+    const int Np = (int)h->Npad, R = h->nranks, me = h->rank;
+    for (long long s = TILE; s < Np; s *= 2) {
+        const int batch = (int)((Np + 2 * s - 1) / (2 * s));
+        const int n2 = (int)((Np - s < s) ? Np - s : s);
+        const int tiles = (int)(s / TILE);
+        if (tiles < R || tiles % R) {                        // small level: recompute everywhere
+            CK(merge_inverse(h, 0, (int)s, n2, batch));
+            continue;
+        }
+        const int wr = (int)(s / R), off = me * wr;
+        const int lim = Np - (int)s;
+        {   // T'[slice rows, :] = Wt_A[slice rows, :] * L21'
+            GemmDesc g = gemm_desc_default();
+            g.A = GemmOperand{bufG(h), bufDinvT(h), off, 0};
+            g.B = GemmOperand{bufF(h), bufNone(), (int)s, 0};
+            g.C = h->F; g.ldc = h->ld; g.c_row0 = off; g.c_col0 = (int)s;
+            g.M = wr; g.N = n2; g.K = (int)s;
+            g.flags = GEMM_KLO_M; g.klo_off = off;
+            g.batch = batch; g.zstep = 2 * (int)s; g.n_lim = lim;
+            CK(launch_gemm(h, g));
+        }
+        {   // W21[:, slice] = -W_C * (T'[slice rows, :])'
+            GemmDesc g = gemm_desc_default();
+            g.A = GemmOperand{bufG(h), bufDinv(h), (int)s, (int)s};
+            g.B = GemmOperand{bufF(h), bufNone(), off, (int)s};
+            g.C = h->G; g.ldc = h->ld; g.c_row0 = (int)s; g.c_col0 = off;
+            g.Ct = h->G; g.ldct = h->ld; g.ct_row0 = off; g.ct_col0 = (int)s;
+            g.M = n2; g.N = wr; g.K = n2;
+            g.alpha = -1.0; g.flags = GEMM_KHI_M;
+            g.batch = batch; g.zstep = 2 * (int)s; g.m_lim = lim; g.k_lim = lim;
+            CK(launch_gemm(h, g));
+        }
+        // exchange the column slices
+        const long long per_rank = (long long)batch * s * wr;
+        if ((size_t)per_rank > h->ag_send_elems || (size_t)per_rank * R > h->ag_recv_elems)
+            return fail(h, GPB200_ECUDA, "inverse_dist: exchange buffers too small");
+        dim3 blk(32, 32), grd((wr + 31) / 32, (unsigned)((s + 31) / 32), (unsigned)batch);
+        h->launches += 2;
+        pack_slices_kernel<<<grd, blk, 0, h->st>>>(h->G, h->ld, h->ag_send, (int)s, wr, off, Np);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev_x, h->st));
+        CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
+        CKN(g_nccl.AllGather(h->ag_send, h->ag_recv, (size_t)per_rank, ncclDouble, h->comm, h->st_comm));
+        CK(cudaEventRecord(h->ev_y, h->st_comm));
+        CK(cudaStreamWaitEvent(h->st, h->ev_y, 0));
+        dim3 grd2((wr + 31) / 32, (unsigned)((s + 31) / 32), (unsigned)(batch * R));
+        unpack_slices_kernel<<<grd2, blk, 0, h->st>>>(h->G, h->ld, h->ag_recv, per_rank, (int)s, wr, Np, R, me);
+        CK(cudaGetLastError());
+    }
+    // W'W on this rank's tile rows only (K^-1 stays distributed; the trace needs no more)
+    GemmDesc g = gemm_desc_default();
+    g.A = GemmOperand{bufG(h), bufDinvT(h), 0, 0};
+    g.B = GemmOperand{bufG(h), bufDinvT(h), 0, 0};
+    g.C = h->G; g.ldc = h->ld; g.c_row0 = 0; g.c_col0 = 0;
+    g.M = Np; g.N = Np; g.K = Np;
+    g.flags = GEMM_LOWER_ONLY | GEMM_KLO_M;
+    g.bm_mod = R; g.bm_rem = me;
+    CK(launch_gemm(h, g));
+    return GPB200_OK;
+}
+
 // alpha-type solve on device vectors: out = K_y^-1 rhs ; rhs (Npad, zero padded) is destroyed
 cudaError_t solve_device(gpb200_handle* h, double* rhs, double* tmp, double* out) {
     cudaError_t e = trsv_lower_fwd(h->F, h->ld, h->Dinv, rhs, tmp, h->Npad, h->st, &h->launches);
@@ -418,6 +694,15 @@ void gpb200_destroy(gpb200_handle* h) {
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
     for (auto e : h->pev) cudaEventDestroy(e);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_packed[i]) cudaEventDestroy(h->ev_packed[i]);
+        if (h->ev_bcast[i]) cudaEventDestroy(h->ev_bcast[i]);
+        if (h->ev_unpacked[i]) cudaEventDestroy(h->ev_unpacked[i]);
+    }
+    if (h->ev_x) cudaEventDestroy(h->ev_x);
+    if (h->ev_y) cudaEventDestroy(h->ev_y);
+    if (h->st_comm) cudaStreamDestroy(h->st_comm);
     if (h->st && h->own_stream) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -430,6 +715,11 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
         h->nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
     if (!strcmp(key, "gemm")) { h->gemm_impl = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "dist_nb")) {
+        if (value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048 && value != 4096)
+            return fail(h, GPB200_EINVAL, "dist_nb must be 128 * 2^k <= 4096");
+        h->dist_nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
+    }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "profile")) {
         h->profile = value ? 1 : 0;
@@ -585,9 +875,21 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
 
     CK(cudaEventRecord(h->ev0, h->st));
     ++h->launches;
-    CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld, h->st));
-    CK(cudaEventRecord(h->ev1, h->st));
-    CK(cholesky(h));
+    if (h->nranks > 1) {
+        int rc = dist_alloc(h);
+        if (rc) return rc;
+        int NBd = TILE;
+        while (NBd < h->dist_nb && NBd < h->Npad) NBd *= 2;
+        CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld,
+                             h->st, NBd / TILE, h->nranks, h->rank));
+        CK(cudaEventRecord(h->ev1, h->st));
+        rc = cholesky_dist(h);
+        if (rc) return rc;
+    } else {
+        CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld, h->st));
+        CK(cudaEventRecord(h->ev1, h->st));
+        CK(cholesky(h));
+    }
     CK(cudaEventRecord(h->ev2, h->st));
     int info = 0;
     CK(cudaMemcpyAsync(&info, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -657,7 +959,8 @@ int gpb200_grad_prepare(gpb200_handle* h) {
     if (h->inv_ready) return GPB200_OK;
     CK(cudaSetDevice(h->device));
     CK(cudaEventRecord(h->ev0, h->st));
-    CK(inverse_from_factor(h));
+    if (h->nranks > 1) { int rc = inverse_dist(h); if (rc) return rc; }
+    else CK(inverse_from_factor(h));
     CK(cudaEventRecord(h->ev1, h->st));
     CK(cudaStreamSynchronize(h->st));
     profile_collect(h);
@@ -678,7 +981,15 @@ int gpb200_grad_kernel(gpb200_handle* h, const double* alpha, double* dmll_kerne
     }
     CK(cudaEventRecord(h->ev0, h->st));
     h->launches += 2;
-    CK(trace_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st));
+    CK(trace_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
+                    h->nranks, h->rank));
+    if (h->nranks > 1) {                                   // P+1 partial sums, summed over ranks
+        CK(cudaEventRecord(h->ev_x, h->st));
+        CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
+        CKN(g_nccl.AllReduce(h->trace_out, h->trace_out, (size_t)trace_num_acc(h->prog), ncclDouble, ncclSum, h->comm, h->st_comm));
+        CK(cudaEventRecord(h->ev_y, h->st_comm));
+        CK(cudaStreamWaitEvent(h->st, h->ev_y, 0));
+    }
     CK(cudaEventRecord(h->ev1, h->st));
     const int np = h->prog.n_theta;
     std::vector<double> out((size_t)np + 1);
@@ -788,6 +1099,7 @@ int gpb200_get_factor(gpb200_handle* h, double* U) {
 int gpb200_get_inverse(gpb200_handle* h, double* Kinv) {
     if (!h || !Kinv) return GPB200_EINVAL;
     if (!h->inv_ready) return fail(h, GPB200_ESTATE, "get_inverse: grad_prepare first");
+    if (h->nranks > 1) return fail(h, GPB200_ESTATE, "get_inverse: K^-1 is distributed over the ranks (tile rows round-robin)");
     CK(cudaSetDevice(h->device));
     const int64_t N = h->N;
     CK(cudaMemcpy2DAsync(Kinv, sizeof(double) * N, h->G, sizeof(double) * h->ld, sizeof(double) * N, N,
@@ -832,10 +1144,36 @@ int gpb200_fp64_peak(gpb200_handle* h, double* tflops_dmma, double* tflops_dfma)
     return GPB200_OK;
 }
 
-int gpb200_nccl_unique_id(char* id128) { (void)id128; return GPB200_ENCCL; }
+int gpb200_nccl_unique_id(char* id128) {
+    if (!id128) return GPB200_EINVAL;
+    if (!nccl_load()) { g_create_error = "libnccl.so.2 could not be loaded"; return GPB200_ENCCL; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return GPB200_ENCCL; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return GPB200_OK;
+}
+
 int gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128) {
-    (void)nranks; (void)rank; (void)id128;
-    return fail(h, GPB200_ENCCL, "multi-GPU path not built in this revision");
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return GPB200_EINVAL;
+    if (nranks & (nranks - 1)) return fail(h, GPB200_EINVAL, "comm_init: number of ranks must be a power of two");
+    if (!nccl_load()) return fail(h, GPB200_ENCCL, "libnccl.so.2 could not be loaded");
+    CK(cudaSetDevice(h->device));
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    CKN(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    if (!h->st_comm) CK(cudaStreamCreateWithFlags(&h->st_comm, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!h->ev_packed[i]) CK(cudaEventCreateWithFlags(&h->ev_packed[i], cudaEventDisableTiming));
+        if (!h->ev_bcast[i]) CK(cudaEventCreateWithFlags(&h->ev_bcast[i], cudaEventDisableTiming));
+        if (!h->ev_unpacked[i]) CK(cudaEventCreateWithFlags(&h->ev_unpacked[i], cudaEventDisableTiming));
+    }
+    if (!h->ev_x) CK(cudaEventCreateWithFlags(&h->ev_x, cudaEventDisableTiming));
+    if (!h->ev_y) CK(cudaEventCreateWithFlags(&h->ev_y, cudaEventDisableTiming));
+    h->nranks = nranks; h->rank = rank;
+    h->factored = h->inv_ready = false;
+    return GPB200_OK;
 }
 
 }  // extern "C"

@@ -10,12 +10,13 @@
 //   info                             <- p + j + 1 of the first non-positive pivot (atomicMin)
 //
 // Design: the tile lives in REGISTERS (512 threads x 32 doubles: thread (warp w, lane l) owns rows
-// w+16a, columns l+32c).  Step j publishes the unscaled column j to shared memory, one
-// __syncthreads, then every thread applies the rank-1 update to its registers.  The published
-// columns stay in shared memory (lower triangle of S) and drive the second phase, a right-looking
-// triangular inversion whose rows W[i,:] are published into the strict upper triangle of the same
-// array (S[n][i+1]).  One barrier per step, 256 steps per tile, no shared-memory bank conflicts
-// (row stride 129 doubles).
+// l+32a, columns w+16c).  Rows across lanes / columns across warps makes every per-step predicate
+// warp-uniform and lets a whole warp publish a column: step j publishes the unscaled column j to
+// shared memory (S[m][j], m >= j), one __syncthreads, then every thread applies the rank-1 update
+// to its registers (entries above the diagonal are never read and may hold garbage).  Phase 2
+// computes W = L^-1 from W L = I by backward column elimination in the same register layout,
+// publishing column j of W into the strict upper triangle (S[j][m+1]).  One barrier per step, 256
+// steps per tile, no divergent branches, no shared-memory bank conflicts (row stride 129 doubles).
 #include "potrf_base.cuh"
 #include <math.h>
 
@@ -34,28 +35,30 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
     const int p = p0 + blockIdx.x * tile_stride;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 
-    double a[8][4];
-#pragma unroll
-    for (int ia = 0; ia < 8; ++ia) {
-        const int m = w + 16 * ia;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int n = l + 32 * c;
-            a[ia][c] = (n <= m) ? G[(long long)(p + m) * ldg + p + n] : 0.0;
-        }
+    // coalesced tile load through shared memory, then into the register layout
+    for (int idx = threadIdx.x; idx < T * T; idx += NTH) {
+        const int m = idx >> 7, n = idx & 127;
+        S[m * LDS + n] = (n <= m) ? G[(long long)(p + m) * ldg + p + n] : 0.0;
     }
+    __syncthreads();
+    double a[4][8];
+#pragma unroll
+    for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[ia][c] = S[(l + 32 * ia) * LDS + w + 16 * c];
+    __syncthreads();
 
     // ---- phase 1: right-looking Cholesky, unscaled columns published to S[m][j] (m >= j) ----
 #pragma unroll 1
     for (int j = 0; j < T; ++j) {
-        const int jc = j >> 5, jl = j & 31;
-        if (l == jl) {
+        if (w == (j & 15)) {                       // warp-uniform: this warp owns column j
+            const int cj = j >> 4;
 #pragma unroll
-            for (int ia = 0; ia < 8; ++ia) {
-                const int m = w + 16 * ia;
+            for (int ia = 0; ia < 4; ++ia) {
                 double v = a[ia][0];
 #pragma unroll
-                for (int c = 1; c < 4; ++c) if (c == jc) v = a[ia][c];
+                for (int c = 1; c < 8; ++c) if (c == cj) v = a[ia][c];
+                const int m = l + 32 * ia;
                 if (m >= j) S[m * LDS + j] = v;
             }
         }
@@ -67,22 +70,19 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
         }
         const double invd = __drcp_rn(d);
         if (threadIdx.x == 0) rs[j] = d;          // pivot; turned into 1/sqrt(d) after the loop
-        // column values this lane needs (live chunks only: 32c+31 > j)
-        double cn[4];
+        double lm[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cn[c] = (32 * c + 31 > j) ? S[(l + 32 * c) * LDS + j] : 0.0;
+        for (int ia = 0; ia < 4; ++ia) {
+            const int m = l + 32 * ia;
+            lm[ia] = (m > j) ? S[m * LDS + j] * invd : 0.0;
+        }
 #pragma unroll
-        for (int ia = 0; ia < 8; ++ia) {
-            const int m = w + 16 * ia;                 // warp-uniform
-            if (m > j) {
-                const double lm = S[m * LDS + j] * invd;
+        for (int c = 0; c < 8; ++c) {
+            const int n = w + 16 * c;
+            if (n > j) {                           // warp-uniform
+                const double cn = S[n * LDS + j];  // broadcast
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (32 * c + 31 > j && 32 * c <= m) {      // warp-uniform: chunk has live columns
-                        const int n = l + 32 * c;
-                        if (n > j && n <= m) a[ia][c] -= lm * cn[c];
-                    }
-                }
+                for (int ia = 0; ia < 4; ++ia) a[ia][c] = fma(-lm[ia], cn, a[ia][c]);
             }
         }
     }
@@ -93,46 +93,50 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
         rs[threadIdx.x] = 1.0 / sqrt(d);
     }
     __syncthreads();
-
-    // ---- write L = S .* rs (lower triangle) ----
+    // scale the published columns in place: S[m][j] = L[m][j], and write L (lower triangle)
     for (int idx = threadIdx.x; idx < T * T; idx += NTH) {
         const int m = idx >> 7, j = idx & 127;
-        if (j <= m) F[(long long)(p + m) * ldf + p + j] = S[m * LDS + j] * rs[j];
+        if (j <= m) {
+            const double v = S[m * LDS + j] * rs[j];
+            S[m * LDS + j] = v;
+            F[(long long)(p + m) * ldf + p + j] = v;
+        }
     }
+    __syncthreads();
 
-    // ---- phase 2: W = L^-1 by right-looking elimination on R (init I), rows published to S[n][i+1] ----
+    // ---- phase 2: W L = I, backward over columns; column j of W published to S[j][m+1] (m >= j) ----
 #pragma unroll
-    for (int ia = 0; ia < 8; ++ia) {
-        const int m = w + 16 * ia;
+    for (int ia = 0; ia < 4; ++ia)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) a[ia][c] = (l + 32 * c == m) ? 1.0 : 0.0;
-    }
+        for (int c = 0; c < 8; ++c) a[ia][c] = (l + 32 * ia == w + 16 * c) ? 1.0 : 0.0;
 #pragma unroll 1
-    for (int i = 0; i < T; ++i) {
-        const double rsi = rs[i];
-        if (w == (i & 15)) {
-            const int a0 = i >> 4;
+    for (int j = T - 1; j >= 0; --j) {
+        if (w == (j & 15)) {
+            const int cj = j >> 4;
+            const double rsj = rs[j];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int n = l + 32 * c;
-                double v = a[0][c];
+            for (int ia = 0; ia < 4; ++ia) {
+                double v = a[ia][0];
 #pragma unroll
-                for (int ia = 1; ia < 8; ++ia) if (ia == a0) v = a[ia][c];
-                if (n <= i) S[n * LDS + i + 1] = v * rsi;         // W[i][n]
+                for (int c = 1; c < 8; ++c) if (c == cj) v = a[ia][c];
+                const int m = l + 32 * ia;
+                if (m >= j) S[j * LDS + m + 1] = v * rsj;          // W[m][j]
             }
         }
         __syncthreads();
-        double wn[4];
+        double wm[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wn[c] = (32 * c <= i && l + 32 * c <= i) ? S[(l + 32 * c) * LDS + i + 1] : 0.0;
+        for (int ia = 0; ia < 4; ++ia) {
+            const int m = l + 32 * ia;
+            wm[ia] = (m >= j) ? S[j * LDS + m + 1] : 0.0;
+        }
 #pragma unroll
-        for (int ia = 0; ia < 8; ++ia) {
-            const int m = w + 16 * ia;
-            if (m > i) {
-                const double lmi = S[m * LDS + i] * rsi;          // L[m][i]
+        for (int c = 0; c < 8; ++c) {
+            const int kk = w + 16 * c;
+            if (kk < j) {                          // warp-uniform
+                const double ljk = S[j * LDS + kk];                // L[j][k], broadcast
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (32 * c <= i) a[ia][c] -= lmi * wn[c];     // wn == 0 for n > i
+                for (int ia = 0; ia < 4; ++ia) a[ia][c] = fma(-wm[ia], ljk, a[ia][c]);
             }
         }
     }

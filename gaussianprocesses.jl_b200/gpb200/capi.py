@@ -48,7 +48,7 @@ _SIGNATURES = {
     "gpb200_dgemm_nt_device": (C.c_int, [_H, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int64,
                                          C.c_int, C.c_int, _dp]),
-    "gpb200_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "gpb200_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "gpb200_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
 }
 
@@ -223,6 +223,21 @@ class Engine:
     def set_stream(self, cuda_stream):
         """Run on the caller's CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream); 0/None = private."""
         self._check(self._lib.gpb200_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)), "set_stream")
+
+    # -- multi-GPU (one process per GPU) -------------------------------------------------------
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        rc = self._lib.gpb200_nccl_unique_id(C.cast(buf, C.c_void_p))
+        if rc != OK:
+            raise RuntimeError("gpb200_nccl_unique_id failed (%d)" % rc)
+        return buf.raw
+
+    def comm_init(self, nranks, rank, id128):
+        if len(id128) != 128:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        ib = C.create_string_buffer(bytes(id128), 128)
+        self._check(self._lib.gpb200_comm_init(self._h, int(nranks), int(rank), C.cast(ib, C.c_char_p)), "comm_init")
+        self.nranks, self.rank = int(nranks), int(rank)
 
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()

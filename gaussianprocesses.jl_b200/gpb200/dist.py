@@ -1,0 +1,34 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed only carries the 128-byte
+NCCL unique id and the timing reductions; the data path (panel broadcasts, slice all-gathers, the
+P+1-scalar all-reduce) runs inside libgpb200 on its own NCCL communicator over NVLink."""
+
+
+def broadcast_bytes(payload_or_none, src=0):
+    """rank `src` passes bytes, the others None; everyone gets the bytes (any backend, incl. gloo)."""
+    import torch.distributed as dist
+    obj = [payload_or_none if dist.get_rank() == src else None]
+    dist.broadcast_object_list(obj, src=src)
+    return obj[0]
+
+
+def init_engine_comm(engine):
+    """Join `engine` (one per rank) into one NCCL communicator spanning the default process group."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 1, 0
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = broadcast_bytes(engine.nccl_unique_id() if rank == 0 else None, src=0)
+    engine.comm_init(world, rank, uid)
+    return world, rank
+
+
+def max_over_ranks(value):
+    """max of a python float over the default process group (device-side for nccl, host for gloo)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -71,6 +71,15 @@ class GPE:
         self._eng.set_data(self._xpm)
         return self
 
+    def init_distributed(self):
+        """Multi-GPU: join this rank's engine into the NCCL communicator of the torch.distributed
+        default group (one process per GPU).  Every later update_*/predict call is collective."""
+        from .dist import init_engine_comm
+        world, rank = init_engine_comm(self._eng)
+        if world > 1:
+            self.update_target()
+        return world, rank
+
     def _sync_kernel(self):
         ops, dims, theta, exposed = flatten(self.kernel, self.dim)
         self._exposed = exposed

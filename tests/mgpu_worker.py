@@ -1,0 +1,64 @@
+"""Worker for the multi-GPU parity test: torchrun --nproc-per-node R tests/mgpu_worker.py
+Each rank builds the same GPE, joins the NCCL communicator, evaluates mll + gradient + predict_f and
+rank 0 compares with the CPU oracle (same tolerances as the single-GPU parity tests)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gaussianprocesses.jl_b200"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import gpb200
+    from oracle import gp_oracle as orc
+
+    rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for (N, d, dist_nb, kern, spec) in [
+        (1500, 3, 256, gpb200.SEIso(0.3, 0.1), None),
+        (2300, 2, 128, gpb200.Mat32Iso(0.2, 0.1) + gpb200.RQIso(0.4, -0.3, 0.2), None),
+        (4000, 4, 1024, gpb200.SEIso(0.4, 0.2), None),
+    ]:
+        rng = np.random.default_rng(N)
+        X = rng.standard_normal((N, d)); y = np.sin(X.sum(axis=1)) + 0.1 * rng.standard_normal(N)
+        Xs = rng.standard_normal((50, d))
+        gp = gpb200.GPE(X.T, y, gpb200.MeanConst(0.2), kern, -0.5, device=local)
+        gp._eng.set_option("dist_nb", dist_nb)
+        gp.init_distributed()
+        gp.update_target_and_dtarget()
+        mu, s2 = gp.predict_f(Xs.T)
+        if rank == 0:
+            o = orc.mll_and_dmll(kern.spec(), X, y, -0.5, ("MeanConst", 0.2))
+            mo, vo = orc.predict_f(kern.spec(), X, o, Xs, ("MeanConst", 0.2))
+            e_mll = abs(gp.mll - o["mll"]) / abs(o["mll"])
+            e_al = np.max(np.abs(gp.alpha - o["alpha"])) / np.max(np.abs(o["alpha"]))
+            e_g = np.max(np.abs(gp.dmll - o["dmll"]) / (np.abs(o["dmll"]) + 1e-10))
+            e_mu = np.max(np.abs(mu - mo)) / np.max(np.abs(mo))
+            e_v = np.max(np.abs(s2 - vo)) / np.max(np.abs(vo))
+            good = e_mll < 1e-10 and e_al < 1e-10 and e_g < 1e-8 and e_mu < 1e-10 and e_v < 1e-10
+            print("MGPU world=%d N=%d nb=%d: mll %.2e alpha %.2e dmll %.2e mu %.2e var %.2e -> %s"
+                  % (world, N, dist_nb, e_mll, e_al, e_g, e_mu, e_v, "OK" if good else "FAIL"), flush=True)
+            ok = ok and good
+        # every rank must hold the same results
+        t = torch.tensor([gp.mll] + list(gp.dmll), dtype=torch.float64, device="cuda")
+        tmax = t.clone(); tmin = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        if rank == 0 and not torch.equal(tmax, tmin):
+            print("MGPU ranks disagree", (tmax - tmin).abs().max().item(), flush=True)
+            ok = False
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_RESULT", "PASS" if ok else "FAIL", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
