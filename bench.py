@@ -245,7 +245,7 @@ def main():
     tp = eng.timings()
     eng.set_option("profile", 0)
     if tp["gemm_ms"] > 0:
-        alg = float(N) ** 3                                     # N^3/3 Cholesky + 2N^3/3 inverse, all in this kernel
+        alg = float(N) ** 3 / world                             # N^3/3 Cholesky + 2N^3/3 inverse, all in this kernel (per rank)
         achieved = alg / (tp["gemm_ms"] * 1e-3) * 1e-12
         traffic = None
         tj = os.path.join(ROOT, "profiles", "gemm_traffic.json")

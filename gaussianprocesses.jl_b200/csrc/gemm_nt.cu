@@ -40,7 +40,7 @@ struct GemmKP {
     int M, N, K;
     int flags, zstep, m_lim, n_lim, k_lim;
     int a_has_sub, b_has_sub;
-    int klo_off, bm_mod, bm_rem;
+    int klo_off, bm_mod, bm_rem, bn_mod, bn_rem;
     double alpha, beta;
 };
 
@@ -73,7 +73,8 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
     } else {
         t.bn = blockIdx.x; t.bm = blockIdx.y;
     }
-    t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem);
+    t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem) &&
+              (p.bn_mod <= 1 || (t.bn % p.bn_mod) == p.bn_rem);
     t.kt_lo = (p.flags & GEMM_KLO_M) ? (p.klo_off + t.bm * BM) / BK : 0;
     int hi = Kz > 0 ? Kz / BK : 0;
     if (p.flags & GEMM_KHI_M) hi = min(hi, (t.bm + 1) * (BM / BK));
@@ -372,7 +373,7 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     p.M = d.M; p.N = d.N; p.K = d.K;
     p.flags = d.flags; p.zstep = d.zstep; p.m_lim = d.m_lim; p.n_lim = d.n_lim; p.k_lim = d.k_lim;
     p.a_has_sub = d.A.sub.base != nullptr; p.b_has_sub = d.B.sub.base != nullptr;
-    p.klo_off = d.klo_off; p.bm_mod = d.bm_mod; p.bm_rem = d.bm_rem;
+    p.klo_off = d.klo_off; p.bm_mod = d.bm_mod; p.bm_rem = d.bm_rem; p.bn_mod = d.bn_mod; p.bn_rem = d.bn_rem;
     p.alpha = d.alpha; p.beta = d.beta;
     if (d.M <= 0 || d.N <= 0) return cudaSuccess;
     if ((d.M % BM) || (d.N % BN) || (d.K % BK)) return cudaErrorInvalidValue;

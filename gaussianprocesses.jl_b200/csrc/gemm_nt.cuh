@@ -40,6 +40,7 @@ struct GemmDesc {
     int m_lim, n_lim, k_lim;   // per-batch clipping: M_z = min(M, m_lim - z*zstep) etc. (<=0: skip)
     int klo_off;        // GEMM_KLO_M: k starts at klo_off + bm*128 (row slice of a triangular operand)
     int bm_mod, bm_rem; // multi-GPU work split: only tile rows with bm % bm_mod == bm_rem (bm_mod <= 1: all)
+    int bn_mod, bn_rem; // same for tile columns
 };
 
 static inline GemmDesc gemm_desc_default() {

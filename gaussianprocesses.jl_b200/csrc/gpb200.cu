@@ -89,7 +89,7 @@ struct gpb200_handle {
     int nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
     cudaStream_t st_comm = nullptr;
-    int dist_nb = 1024;                        // width of an owned block column
+    int dist_nb = 0;                           // width of an owned block column; 0 = auto (~Npad/(4*nranks))
     double* pack[2] = {nullptr, nullptr};      // panel staging (double buffered)
     size_t pack_elems = 0;
     cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_bcast[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr};
@@ -191,8 +191,10 @@ double gemm_exec_flops(const GemmDesc& d) {
         if (Mz <= 0 || Nz <= 0 || Kz <= 0) continue;
         const int tm = Mz / TILE, tn = Nz / TILE;
         for (int bm = 0; bm < tm; ++bm) {
+            if (d.bm_mod > 1 && (bm % d.bm_mod) != d.bm_rem) continue;
             const int bn_hi = (d.flags & GEMM_LOWER_ONLY) ? std::min(bm + 1, tn) : tn;
             for (int bn = 0; bn < bn_hi; ++bn) {
+                if (d.bn_mod > 1 && (bn % d.bn_mod) != d.bn_rem) continue;
                 int lo = (d.flags & GEMM_KLO_M) ? bm * TILE : 0;
                 int hi = Kz;
                 if (d.flags & GEMM_KHI_M) hi = std::min(hi, (bm + 1) * TILE);
@@ -363,44 +365,61 @@ cudaError_t inverse_from_factor(gpb200_handle* h) {
 //   W'W + trace     : tile rows dealt round-robin; only the P+1 partial sums are all-reduced, K^-1
 //                     itself is never exchanged.
 // ================================================================================================
+// rank q owns the 128-wide tile columns t with t % nranks == q of every W21 block; its "slice" is
+// the concatenation of those tile columns (local column jl <-> global column ((jl/128)*nranks+q)*128 + jl%128)
 __global__ void pack_slices_kernel(const double* __restrict__ G, long long ld, double* __restrict__ out,
-                                   int s, int wr, int off, int Np) {
+                                   int s, int wr, int nranks, int self, int Np) {
     const int z = blockIdx.z;
     const int p = z * 2 * s;
     const int n2 = min(s, Np - p - s);
-    const int i = blockIdx.y * 32 + threadIdx.y, j = blockIdx.x * 32 + threadIdx.x;
-    if (n2 <= 0 || i >= n2 || j >= wr) return;
-    out[(long long)z * s * wr + (long long)i * wr + j] = G[(long long)(p + s + i) * ld + p + off + j];
+    const int i = blockIdx.y * 32 + threadIdx.y, jl = blockIdx.x * 32 + threadIdx.x;
+    if (n2 <= 0 || i >= n2 || jl >= wr) return;
+    const int gj = ((jl >> 7) * nranks + self) * 128 + (jl & 127);
+    out[(long long)z * s * wr + (long long)i * wr + jl] = G[(long long)(p + s + i) * ld + p + gj];
 }
-// scatter the gathered W21 column slices of all other ranks into G (lower block) and, transposed, into
+// scatter the gathered W21 slices of all other ranks into G (lower block) and, transposed, into
 // G's strict-upper block
 __global__ void unpack_slices_kernel(double* __restrict__ G, long long ld, const double* __restrict__ in,
                                      long long per_rank, int s, int wr, int Np, int nranks, int self) {
     __shared__ double tile[32][33];
-    const int z = blockIdx.z % ((Np + 2 * s - 1) / (2 * s));
-    const int q = blockIdx.z / ((Np + 2 * s - 1) / (2 * s));
+    const int batch = (Np + 2 * s - 1) / (2 * s);
+    const int z = blockIdx.z % batch;
+    const int q = blockIdx.z / batch;
     if (q == self) return;
     const int p = z * 2 * s;
     const int n2 = min(s, Np - p - s);
     if (n2 <= 0) return;
     const double* src = in + (long long)q * per_rank + (long long)z * s * wr;
-    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;            // 32 | 128: a block never straddles tiles
     if (i0 >= n2 || j0 >= wr) return;
-    const int i = i0 + threadIdx.y, j = j0 + threadIdx.x;
+    const int i = i0 + threadIdx.y, jl = j0 + threadIdx.x;
     double v = 0.0;
-    if (i < n2 && j < wr) {
-        v = src[(long long)i * wr + j];
-        G[(long long)(p + s + i) * ld + p + q * wr + j] = v;
+    if (i < n2 && jl < wr) {
+        v = src[(long long)i * wr + jl];
+        const int gj = ((jl >> 7) * nranks + q) * 128 + (jl & 127);
+        G[(long long)(p + s + i) * ld + p + gj] = v;
     }
     tile[threadIdx.y][threadIdx.x] = v;
     __syncthreads();
-    const int ti = i0 + threadIdx.x, tj = j0 + threadIdx.y;          // transposed: row = column slice index
-    if (ti < n2 && tj < wr) G[(long long)(p + q * wr + tj) * ld + p + s + ti] = tile[threadIdx.x][threadIdx.y];
+    const int ti = i0 + threadIdx.x, tjl = j0 + threadIdx.y;
+    if (ti < n2 && tjl < wr) {
+        const int gj = ((tjl >> 7) * nranks + q) * 128 + (tjl & 127);
+        G[(long long)(p + gj) * ld + p + s + ti] = tile[threadIdx.x][threadIdx.y];
+    }
+}
+
+int dist_block(gpb200_handle* h) {
+    int NB = TILE;
+    if (h->dist_nb > 0) { while (NB < h->dist_nb && NB < h->Npad) NB *= 2; return NB; }
+    const long long target = h->Npad / (4LL * h->nranks);           // ~4 block columns per rank
+    while (NB * 2 <= target && NB < 4096) NB *= 2;
+    return NB < 256 ? (h->Npad >= 256 ? 256 : TILE) : NB;
 }
 
 int dist_alloc(gpb200_handle* h) {
     const size_t Np = (size_t)h->Npad;
-    const size_t need_pack = Np * (size_t)h->dist_nb + 2 * (size_t)h->dist_nb * TILE + (size_t)h->dist_nb + 16;
+    const size_t nbw = (size_t)dist_block(h);
+    const size_t need_pack = Np * nbw + 2 * nbw * TILE + nbw + 16;
     if (need_pack > h->pack_elems) {
         for (int i = 0; i < 2; ++i) {
             if (h->pack[i]) cudaFree(h->pack[i]);
@@ -449,8 +468,7 @@ cudaError_t panel_pack(gpb200_handle* h, int p, int n, double* buf, bool unpack)
 
 int cholesky_dist(gpb200_handle* h) {
     const int Np = (int)h->Npad, R = h->nranks, me = h->rank;
-    int NB = TILE;
-    while (NB < h->dist_nb && NB < Np) NB *= 2;
+    const int NB = dist_block(h);
     const int nblk = (Np + NB - 1) / NB;
     auto bp = [&](int b) { return b * NB; };
     auto bn = [&](int b) { return std::min(NB, Np - b * NB); };
@@ -511,36 +529,40 @@ int inverse_dist(gpb200_handle* h) {
             CK(merge_inverse(h, 0, (int)s, n2, batch));
             continue;
         }
-        const int wr = (int)(s / R), off = me * wr;
+        const int wr = (int)(s / R);
         const int lim = Np - (int)s;
-        {   // T'[slice rows, :] = Wt_A[slice rows, :] * L21'
+        {   // T'[own tile rows, :] = Wt_A[own tile rows, :] * L21'
             GemmDesc g = gemm_desc_default();
-            g.A = GemmOperand{bufG(h), bufDinvT(h), off, 0};
+            g.A = GemmOperand{bufG(h), bufDinvT(h), 0, 0};
             g.B = GemmOperand{bufF(h), bufNone(), (int)s, 0};
-            g.C = h->F; g.ldc = h->ld; g.c_row0 = off; g.c_col0 = (int)s;
-            g.M = wr; g.N = n2; g.K = (int)s;
-            g.flags = GEMM_KLO_M; g.klo_off = off;
+            g.C = h->F; g.ldc = h->ld; g.c_row0 = 0; g.c_col0 = (int)s;
+            g.M = (int)s; g.N = n2; g.K = (int)s;
+            g.flags = GEMM_KLO_M;
+            g.bm_mod = R; g.bm_rem = me;
             g.batch = batch; g.zstep = 2 * (int)s; g.n_lim = lim;
             CK(launch_gemm(h, g));
         }
-        {   // W21[:, slice] = -W_C * (T'[slice rows, :])'
+        {   // W21[:, own tile columns] = -W_C * (T'[own tile rows, :])'
             GemmDesc g = gemm_desc_default();
             g.A = GemmOperand{bufG(h), bufDinv(h), (int)s, (int)s};
-            g.B = GemmOperand{bufF(h), bufNone(), off, (int)s};
-            g.C = h->G; g.ldc = h->ld; g.c_row0 = (int)s; g.c_col0 = off;
-            g.Ct = h->G; g.ldct = h->ld; g.ct_row0 = off; g.ct_col0 = (int)s;
-            g.M = n2; g.N = wr; g.K = n2;
+            g.B = GemmOperand{bufF(h), bufNone(), 0, (int)s};
+            g.C = h->G; g.ldc = h->ld; g.c_row0 = (int)s; g.c_col0 = 0;
+            g.Ct = h->G; g.ldct = h->ld; g.ct_row0 = 0; g.ct_col0 = (int)s;
+            g.M = n2; g.N = (int)s; g.K = n2;
             g.alpha = -1.0; g.flags = GEMM_KHI_M;
+            g.bn_mod = R; g.bn_rem = me;
             g.batch = batch; g.zstep = 2 * (int)s; g.m_lim = lim; g.k_lim = lim;
             CK(launch_gemm(h, g));
         }
         // exchange the column slices
-        const long long per_rank = (long long)batch * s * wr;
+        long long rows_total = 0;                                   // sum over problems of n2_z (only the last is short)
+        for (int z = 0; z < batch; ++z) rows_total += std::max(0LL, std::min((long long)s, (long long)Np - z * 2 * s - s));
+        const long long per_rank = rows_total * wr;
         if ((size_t)per_rank > h->ag_send_elems || (size_t)per_rank * R > h->ag_recv_elems)
             return fail(h, GPB200_ECUDA, "inverse_dist: exchange buffers too small");
         dim3 blk(32, 32), grd((wr + 31) / 32, (unsigned)((s + 31) / 32), (unsigned)batch);
         h->launches += 2;
-        pack_slices_kernel<<<grd, blk, 0, h->st>>>(h->G, h->ld, h->ag_send, (int)s, wr, off, Np);
+        pack_slices_kernel<<<grd, blk, 0, h->st>>>(h->G, h->ld, h->ag_send, (int)s, wr, R, me, Np);
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev_x, h->st));
         CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
@@ -678,6 +700,8 @@ int gpb200_create(gpb200_handle** out, int device) {
     if ((e = gemm_nt_init()) != cudaSuccess) return bail("gemm_nt_init", e);
     const char* env = getenv("GPB200_GEMM");
     if (env) h->gemm_impl = atoi(env);
+    env = getenv("GPB200_DIST_NB");
+    if (env) { int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096) h->dist_nb = v; }
     env = getenv("GPB200_NB");
     if (env) { int v = atoi(env); if (v == 0 || v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096) h->nb = v; }
     *out = h;
@@ -716,8 +740,8 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "gemm")) { h->gemm_impl = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "dist_nb")) {
-        if (value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048 && value != 4096)
-            return fail(h, GPB200_EINVAL, "dist_nb must be 128 * 2^k <= 4096");
+        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048 && value != 4096)
+            return fail(h, GPB200_EINVAL, "dist_nb must be 0 (auto) or 128 * 2^k <= 4096");
         h->dist_nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
@@ -878,8 +902,7 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
     if (h->nranks > 1) {
         int rc = dist_alloc(h);
         if (rc) return rc;
-        int NBd = TILE;
-        while (NBd < h->dist_nb && NBd < h->Npad) NBd *= 2;
+        const int NBd = dist_block(h);
         CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld,
                              h->st, NBd / TILE, h->nranks, h->rank));
         CK(cudaEventRecord(h->ev1, h->st));
