@@ -99,6 +99,24 @@ struct gpb200_handle {
     std::string err;
 };
 
+
+// ---- FITC (sparse/fully_indep_train_conditional.jl): two dense M x M sub-engines + N-chunk streaming ----
+struct gpb200_fitc {
+    gpb200_handle* eu = nullptr;     // K_uu  (+1e-10 I)            -> L_uu
+    gpb200_handle* es = nullptr;     // Sigma_QR = K_uf L^-1 K_fu + K_uu (+1e-10 I) -> L_s
+    int device = 0;
+    int64_t N = 0, M = 0, Mpad = 0, Nc = 0;
+    int d = 0;
+    double *x = nullptr, *xs = nullptr, *lam = nullptr, *y = nullptr, *alpha = nullptr, *tmpn = nullptr;
+    double *w = nullptr, *tmpc = nullptr, *zeroc = nullptr, *tmpc2 = nullptr;          // Nc
+    double *bvec = nullptr, *uvec = nullptr, *tmpm = nullptr, *rhsm = nullptr, *scal = nullptr;   // Mpad
+    double *bufA = nullptr, *bufB = nullptr;   // Nc x Mpad (K_fu chunk) ; Mpad x Nc (K_uf chunk)
+    CUtensorMap mapA{}, mapB{}, mapB2{};
+    double noise_var = 0.0;
+    bool has_data = false, has_kernel = false, factored = false, alpha_ready = false;
+    std::string err;
+};
+
 namespace {
 
 // ---- NCCL, bound at run time (dlopen) so that single-GPU use has no NCCL dependency -------------
@@ -629,33 +647,58 @@ int ensure_predict_ws(gpb200_handle* h, int64_t Mc, bool want_cov) {
     return GPB200_OK;
 }
 
-// Vt[:, c0..c0+n) <- solve against L[c0.., c0..] in place on the predict buffer (rows = Mpad):
-// recursive blocked TRSM, leaves multiply by the inverted 128-tile, updates are NT GEMMs.
-cudaError_t trsm_rec(gpb200_handle* h, int Mpad, int c0, int n) {
-    GemmBuf bk{h->tma_ok ? &h->mapKst : nullptr, h->Kst, h->Npad};
+// Vt[:, c0..c0+n) <- solve against L[c0.., c0..] of handle h, in place on a row-major buffer
+// (`rows` x h->Npad, leading dimension ldk): recursive blocked TRSM, leaves multiply by the inverted
+// 128-tile, updates are NT GEMMs.  (whiten!, PDMats: x <- U^-T x.)
+cudaError_t trsm_rec_buf(gpb200_handle* h, GemmBuf bk, int rows, int c0, int n) {
+    double* kb = const_cast<double*>(bk.base);
     if (n == TILE) {
         GemmDesc g = gemm_desc_default();
         g.A = GemmOperand{bk, bufNone(), 0, c0};
         g.B = GemmOperand{bufDinv(h), bufNone(), c0, 0};
-        g.C = h->Kst; g.ldc = h->Npad; g.c_row0 = 0; g.c_col0 = c0;
-        g.M = Mpad; g.N = TILE; g.K = TILE;
+        g.C = kb; g.ldc = bk.ld; g.c_row0 = 0; g.c_col0 = c0;
+        g.M = rows; g.N = TILE; g.K = TILE;
         return launch_gemm(h, g);
     }
     int n1 = TILE;
     while (n1 * 2 < n) n1 *= 2;
     const int n2 = n - n1;
     cudaError_t e;
-    if ((e = trsm_rec(h, Mpad, c0, n1)) != cudaSuccess) return e;
+    if ((e = trsm_rec_buf(h, bk, rows, c0, n1)) != cudaSuccess) return e;
     {
         GemmDesc g = gemm_desc_default();
         g.A = GemmOperand{bk, bufNone(), 0, c0};
         g.B = GemmOperand{bufF(h), bufNone(), c0 + n1, c0};
-        g.C = h->Kst; g.ldc = h->Npad; g.c_row0 = 0; g.c_col0 = c0 + n1;
-        g.M = Mpad; g.N = n2; g.K = n1;
+        g.C = kb; g.ldc = bk.ld; g.c_row0 = 0; g.c_col0 = c0 + n1;
+        g.M = rows; g.N = n2; g.K = n1;
         g.alpha = -1.0; g.beta = 1.0;
         if ((e = launch_gemm(h, g)) != cudaSuccess) return e;
     }
-    return trsm_rec(h, Mpad, c0 + n1, n2);
+    return trsm_rec_buf(h, bk, rows, c0 + n1, n2);
+}
+cudaError_t trsm_rec(gpb200_handle* h, int Mpad, int c0, int n) {
+    GemmBuf bk{h->tma_ok ? &h->mapKst : nullptr, h->Kst, h->Npad};
+    return trsm_rec_buf(h, bk, Mpad, c0, n);
+}
+
+// factor whatever SPD matrix sits in the lower tiles of h->G (padding must be identity)
+int chol_inplace(gpb200_handle* h) {
+    h->factored = h->inv_ready = h->alpha_ready = false;
+    const int init = INT_MAX;
+    CK(cudaMemcpyAsync(h->info_dev, &init, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CK(cholesky(h));
+    int info = 0;
+    CK(cudaMemcpyAsync(&info, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    profile_collect(h);
+    if (info != INT_MAX) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "matrix is not positive definite; leading minor %d", info);
+        h->err = buf;
+        return info > h->N ? (int)h->N : info;
+    }
+    h->factored = true;
+    return GPB200_OK;
 }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
@@ -1198,5 +1241,281 @@ int gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128) 
     h->factored = h->inv_ready = false;
     return GPB200_OK;
 }
+
+
+// ================================================================================================
+// FITC -- Fully Independent Training Conditional (src/sparse/fully_indep_train_conditional.jl)
+//   update_cK! (:134-156), `\` (:33-36), logdet (:77), dmll_noise (:243-257), predictMVN (:324-332 ->
+//   determ_train_conditional.jl:41-59 -> subsetofregressors.jl:302-321).
+// The reference materialises K_uf (M x N) and several copies; here N is streamed in chunks through two
+// staging buffers and only M x M state persists (H7 of SURVEY.md §7.2): per chunk a cross-Gram, a
+// recursive TRSM against L_uu for diag(Q_ff), and one rank-Nc SYRK into Sigma_QR -- all on the DMMA GEMM.
+// ================================================================================================
+#define FCK(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,       \
+                     cudaGetErrorString(e_));                                                      \
+            f->err = buf_;                                                                         \
+            (void)cudaGetLastError();                                                              \
+            return GPB200_ECUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+#define FSUB(call, who)                                                                            \
+    do {                                                                                           \
+        int rc_ = (call);                                                                          \
+        if (rc_ != GPB200_OK) { f->err = std::string(#call) + ": " + (who)->err; return rc_; }     \
+    } while (0)
+
+void gpb200_fitc_destroy(gpb200_fitc* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    if (f->eu && f->eu->st) cudaStreamSynchronize(f->eu->st);
+    double** ptrs[] = {&f->x, &f->xs, &f->lam, &f->y, &f->alpha, &f->tmpn, &f->w, &f->tmpc, &f->zeroc, &f->tmpc2,
+                       &f->bvec, &f->uvec, &f->tmpm, &f->rhsm, &f->scal, &f->bufA, &f->bufB};
+    for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    if (f->es) { f->es->st = nullptr; f->es->own_stream = false; gpb200_destroy(f->es); }
+    if (f->eu) gpb200_destroy(f->eu);
+    delete f;
+}
+
+int gpb200_fitc_create(gpb200_fitc** out, int device) {
+    if (!out) return GPB200_EINVAL;
+    *out = nullptr;
+    gpb200_fitc* f = new gpb200_fitc();
+    f->device = device;
+    int rc = gpb200_create(&f->eu, device);
+    if (rc == GPB200_OK) rc = gpb200_create(&f->es, device);
+    if (rc != GPB200_OK) { if (f->eu) gpb200_destroy(f->eu); delete f; return rc; }
+    // one stream for both sub-engines
+    cudaStreamDestroy(f->es->st);
+    f->es->st = f->eu->st; f->es->own_stream = false;
+    *out = f;
+    return GPB200_OK;
+}
+
+const char* gpb200_fitc_last_error(gpb200_fitc* f) { return f ? f->err.c_str() : g_create_error.c_str(); }
+
+int gpb200_fitc_set_data(gpb200_fitc* f, int64_t N, int32_t d, const double* x, int64_t ldx, int64_t M,
+                         const double* xu, int64_t ldxu) {
+    if (!f) return GPB200_EINVAL;
+    if (N <= 0 || M <= 0 || d <= 0 || !x || !xu || ldx < d || ldxu < d) { f->err = "fitc_set_data: bad arguments"; return GPB200_EINVAL; }
+    FCK(cudaSetDevice(f->device));
+    FSUB(gpb200_set_data(f->eu, M, d, xu, ldxu), f->eu);
+    FSUB(gpb200_set_data(f->es, M, d, xu, ldxu), f->es);
+    cudaStream_t st = f->eu->st;
+    double** ptrs[] = {&f->x, &f->xs, &f->lam, &f->y, &f->alpha, &f->tmpn, &f->w, &f->tmpc, &f->zeroc, &f->tmpc2,
+                       &f->bvec, &f->uvec, &f->tmpm, &f->rhsm, &f->scal, &f->bufA, &f->bufB};
+    for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    f->N = N; f->M = M; f->d = d; f->Mpad = f->eu->Npad;
+    // chunk of data rows: two staging buffers of ~2 GB each at most
+    int64_t nc = (int64_t)(2.0e9 / (8.0 * (double)f->Mpad)) / TILE * TILE;
+    const int64_t Nceil = (N + TILE - 1) / TILE * TILE;
+    if (nc > 32768) nc = 32768;                       // grid.y limit of the row-scaling kernel
+    if (nc > Nceil) nc = Nceil;
+    if (nc < TILE) nc = TILE;
+    f->Nc = nc;
+    FCK(cudaMalloc(&f->x, sizeof(double) * N * d));
+    FCK(cudaMalloc(&f->xs, sizeof(double) * nc * d));
+    for (double** p : {&f->lam, &f->y, &f->alpha, &f->tmpn}) FCK(cudaMalloc(p, sizeof(double) * (N + TILE)));
+    for (double** p : {&f->w, &f->tmpc, &f->zeroc, &f->tmpc2}) FCK(cudaMalloc(p, sizeof(double) * nc));
+    for (double** p : {&f->bvec, &f->uvec, &f->tmpm, &f->rhsm}) FCK(cudaMalloc(p, sizeof(double) * f->Mpad));
+    FCK(cudaMalloc(&f->scal, sizeof(double) * 16));
+    FCK(cudaMalloc(&f->bufA, sizeof(double) * nc * f->Mpad));
+    FCK(cudaMalloc(&f->bufB, sizeof(double) * nc * f->Mpad));
+    FCK(cudaMemsetAsync(f->zeroc, 0, sizeof(double) * nc, st));
+    FCK(cudaMemcpy2DAsync(f->x, sizeof(double) * d, x, sizeof(double) * ldx, sizeof(double) * d, N, cudaMemcpyHostToDevice, st));
+    if (f->eu->tma_ok) {
+        const bool ok = gemm_make_tensor_map(&f->mapA, f->bufA, nc, f->Mpad, f->Mpad) &&
+                        gemm_make_tensor_map(&f->mapB, f->bufB, f->Mpad, nc, nc) &&
+                        gemm_make_tensor_map(&f->mapB2, f->bufB, nc, f->Mpad, f->Mpad);
+        if (!ok) { f->err = "fitc_set_data: cuTensorMapEncodeTiled failed"; return GPB200_ECUDA; }
+    }
+    FCK(cudaStreamSynchronize(st));
+    f->has_data = true; f->factored = f->alpha_ready = false;
+    return GPB200_OK;
+}
+
+int gpb200_fitc_set_kernel(gpb200_fitc* f, int32_t n_ops, const int32_t* ops, int32_t n_dims, const int32_t* dims,
+                           int32_t n_theta) {
+    if (!f) return GPB200_EINVAL;
+    FSUB(gpb200_set_kernel(f->eu, n_ops, ops, n_dims, dims, n_theta), f->eu);
+    FSUB(gpb200_set_kernel(f->es, n_ops, ops, n_dims, dims, n_theta), f->es);
+    f->has_kernel = true; f->factored = f->alpha_ready = false;
+    return GPB200_OK;
+}
+
+// K_fu chunk (rows r0..r0+nc of x against the inducing points) into bufA [Nc x Mpad]
+static cudaError_t fitc_kfu(gpb200_fitc* f, const double* xrows, int64_t nc) {
+    ++f->eu->launches;
+    return crossgram_launch(f->eu->prog, xrows, f->d, nc, f->Nc, f->eu->x, f->d, f->M, f->Mpad, f->d, f->bufA, f->Mpad, f->eu->st);
+}
+// K_uf chunk into bufB [Mpad x Nc]
+static cudaError_t fitc_kuf(gpb200_fitc* f, const double* xrows, int64_t nc) {
+    ++f->eu->launches;
+    return crossgram_launch(f->eu->prog, f->eu->x, f->d, f->M, f->Mpad, xrows, f->d, nc, f->Nc, f->d, f->bufB, f->Nc, f->eu->st);
+}
+
+int gpb200_fitc_factorize(gpb200_fitc* f, const double* theta, double log_noise) {
+    if (!f) return GPB200_EINVAL;
+    if (!f->has_data || !f->has_kernel) { f->err = "fitc_factorize: set_data and set_kernel first"; return GPB200_ESTATE; }
+    if (!isfinite(log_noise)) { f->err = "fitc_factorize: non-finite logNoise"; return GPB200_EINVAL; }
+    FCK(cudaSetDevice(f->device));
+    f->factored = f->alpha_ready = false;
+    gpb200_handle *eu = f->eu, *es = f->es;
+    cudaStream_t st = eu->st;
+    // K_uu + 1e-10 I and its factor (fitc.jl:139-141)
+    const double ln_off = -1000.0;                          // exp(2*ln) == 0: no noise on K_uu
+    FSUB(gpb200_factorize(eu, theta, &ln_off, 1, 1e-10), eu);
+    // Sigma_QR starts as K_uu (+ the second 1e-10 nugget of make_posdef!, fitc.jl:153)
+    kprog_set_theta(es->prog, theta);
+    for (int i = 0; i < es->prog.n_theta; ++i) es->theta[i] = theta[i];
+    const double zero = 0.0;
+    FCK(cudaMemcpyAsync(es->noise_var, &zero, sizeof(double), cudaMemcpyHostToDevice, st));
+    es->n_noise = 1; es->nugget = 2e-10;
+    ++es->launches;
+    FCK(gram_lower_launch(es->prog, es->x, f->d, f->d, f->M, f->Mpad, es->noise_var, 1, 2e-10, es->G, es->ld, st));
+    f->noise_var = exp(2.0 * log_noise);
+    GemmBuf bA{eu->tma_ok ? &f->mapA : nullptr, f->bufA, f->Mpad};
+    GemmBuf bB{eu->tma_ok ? &f->mapB : nullptr, f->bufB, f->Nc};
+    for (int64_t r0 = 0; r0 < f->N; r0 += f->Nc) {
+        const int64_t nc = std::min(f->Nc, f->N - r0);
+        const double* xr = f->x + r0 * f->d;
+        // Lambda_i = sigma^2 + K_ii - |L_uu^-1 K_ui|^2   (fitc.jl:146-148)
+        FCK(fitc_kfu(f, xr, nc));
+        FCK(trsm_rec_buf(eu, bA, (int)f->Nc, 0, (int)f->Mpad));
+        eu->launches += 3;
+        FCK(kdiag_launch(eu->prog, xr, f->d, nc, f->tmpc, st));
+        FCK(rowvar_launch(f->bufA, f->Mpad, f->tmpc, nc, f->Mpad, f->tmpc2, st));
+        FCK(ew_launch(0, nc, f->lam + r0, f->tmpc2, nullptr, nullptr, f->noise_var, st));
+        // Sigma_QR += K_uf Lambda^-1 K_fu   (fitc.jl:150), as (K_uf Lambda^-1/2)(K_uf Lambda^-1/2)'
+        FCK(fitc_kuf(f, xr, nc));
+        ++eu->launches;
+        FCK(scale_launch(0, f->bufB, f->Nc, f->Mpad, nc, f->lam + r0, st));
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bB, bufNone(), 0, 0};
+        g.B = GemmOperand{bB, bufNone(), 0, 0};
+        g.C = es->G; g.ldc = es->ld; g.M = (int)f->Mpad; g.N = (int)f->Mpad; g.K = (int)f->Nc;
+        g.alpha = 1.0; g.beta = 1.0; g.flags = GEMM_LOWER_ONLY;
+        FCK(launch_gemm(es, g));
+    }
+    int rc = chol_inplace(es);
+    if (rc != GPB200_OK) { f->err = "fitc_factorize (Sigma_QR): " + es->err; return rc; }
+    f->factored = true;
+    return GPB200_OK;
+}
+
+// alpha = Sigma^-1 r (fitc.jl:33-36), logdet (fitc.jl:77), mll (GPE.jl:210)
+int gpb200_fitc_mll(gpb200_fitc* f, const double* y_minus_mean, double* alpha, double* mll, double* logdet) {
+    if (!f || !y_minus_mean || !mll) return GPB200_EINVAL;
+    if (!f->factored) { f->err = "fitc_mll: factorize first"; return GPB200_ESTATE; }
+    FCK(cudaSetDevice(f->device));
+    gpb200_handle *eu = f->eu, *es = f->es;
+    cudaStream_t st = eu->st;
+    FCK(cudaMemcpyAsync(f->y, y_minus_mean, sizeof(double) * f->N, cudaMemcpyHostToDevice, st));
+    // b = K_uf Lambda^-1 r
+    FCK(cudaMemsetAsync(f->bvec, 0, sizeof(double) * f->Mpad, st));
+    for (int64_t r0 = 0; r0 < f->N; r0 += f->Nc) {
+        const int64_t nc = std::min(f->Nc, f->N - r0);
+        FCK(fitc_kuf(f, f->x + r0 * f->d, nc));
+        eu->launches += 3;
+        FCK(cudaMemsetAsync(f->w, 0, sizeof(double) * f->Nc, st));
+        FCK(ew_launch(1, nc, f->w, f->y + r0, f->lam + r0, nullptr, 0.0, st));
+        FCK(rowdot_launch(f->bufB, f->Nc, f->w, f->M, f->Nc, f->tmpm, st));
+        FCK(ew_launch(2, f->M, f->bvec, f->tmpm, nullptr, nullptr, 0.0, st));
+    }
+    // u = Sigma_QR^-1 b   (== get_alpha_u, fitc.jl:279-286)
+    FCK(cudaMemcpyAsync(f->rhsm, f->bvec, sizeof(double) * f->Mpad, cudaMemcpyDeviceToDevice, st));
+    FCK(solve_device(es, f->rhsm, f->tmpm, f->uvec));
+    // alpha = Lambda^-1 (r - K_fu u)
+    for (int64_t r0 = 0; r0 < f->N; r0 += f->Nc) {
+        const int64_t nc = std::min(f->Nc, f->N - r0);
+        FCK(fitc_kfu(f, f->x + r0 * f->d, nc));
+        eu->launches += 2;
+        FCK(rowdot_launch(f->bufA, f->Mpad, f->uvec, nc, f->Mpad, f->tmpc, st));
+        FCK(ew_launch(3, nc, f->alpha + r0, f->y + r0, f->tmpc, f->lam + r0, 0.0, st));
+    }
+    eu->launches += 5;
+    FCK(dot_launch(f->y, f->alpha, f->N, f->scal + 0, st));
+    FCK(sum_launch(es->logd, es->Npad, f->scal + 1, st));
+    FCK(sum_launch(eu->logd, eu->Npad, f->scal + 2, st));
+    FCK(ew_launch(4, f->N, f->tmpn, f->lam, nullptr, nullptr, 0.0, st));
+    FCK(sum_launch(f->tmpn, f->N, f->scal + 3, st));
+    double s[4];
+    FCK(cudaMemcpyAsync(s, f->scal, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+    if (alpha) FCK(cudaMemcpyAsync(alpha, f->alpha, sizeof(double) * f->N, cudaMemcpyDeviceToHost, st));
+    FCK(cudaStreamSynchronize(st));
+    const double ld = s[1] - s[2] + s[3];
+    if (logdet) *logdet = ld;
+    *mll = -(s[0] + ld + LOG2PI * (double)f->N) / 2.0;
+    f->alpha_ready = true;
+    return GPB200_OK;
+}
+
+// dmll_noise (fitc.jl:243-257): sigma^2 * (alpha.alpha - sum 1/Lambda + |L_s^-1 K_uf Lambda^-1|_F^2)
+int gpb200_fitc_grad_noise(gpb200_fitc* f, double* dmll_noise) {
+    if (!f || !dmll_noise) return GPB200_EINVAL;
+    if (!f->factored || !f->alpha_ready) { f->err = "fitc_grad_noise: factorize and mll first"; return GPB200_ESTATE; }
+    FCK(cudaSetDevice(f->device));
+    gpb200_handle *eu = f->eu, *es = f->es;
+    cudaStream_t st = eu->st;
+    GemmBuf bA{eu->tma_ok ? &f->mapA : nullptr, f->bufA, f->Mpad};
+    for (int64_t r0 = 0; r0 < f->N; r0 += f->Nc) {
+        const int64_t nc = std::min(f->Nc, f->N - r0);
+        FCK(fitc_kfu(f, f->x + r0 * f->d, nc));
+        eu->launches += 2;
+        FCK(scale_launch(1, f->bufA, f->Mpad, nc, f->Mpad, f->lam + r0, st));
+        FCK(trsm_rec_buf(es, bA, (int)f->Nc, 0, (int)f->Mpad));
+        FCK(rowvar_launch(f->bufA, f->Mpad, f->zeroc, nc, f->Mpad, f->tmpn + r0, st));     // = -|row|^2
+    }
+    eu->launches += 4;
+    FCK(sum_launch(f->tmpn, f->N, f->scal + 0, st));
+    FCK(dot_launch(f->alpha, f->alpha, f->N, f->scal + 1, st));
+    FCK(ew_launch(5, f->N, f->tmpn, f->lam, nullptr, nullptr, 0.0, st));
+    FCK(sum_launch(f->tmpn, f->N, f->scal + 2, st));
+    double s[3];
+    FCK(cudaMemcpyAsync(s, f->scal, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+    FCK(cudaStreamSynchronize(st));
+    *dmll_noise = f->noise_var * (s[1] - s[2] - s[0]);
+    return GPB200_OK;
+}
+
+// predictive mean / variance (fitc.jl:324-332 -> dtc.jl:41-59 -> sor.jl:302-321):
+//   mu = K_xu u ;  var = k_xx - |L_uu^-1 k_ux|^2 + |L_s^-1 k_ux|^2
+int gpb200_fitc_predict(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ldxs, double* mu, double* var) {
+    if (!f || Ms <= 0 || !xs || ldxs < f->d || !mu) return GPB200_EINVAL;
+    if (!f->factored || !f->alpha_ready) { f->err = "fitc_predict: factorize and mll first"; return GPB200_ESTATE; }
+    FCK(cudaSetDevice(f->device));
+    gpb200_handle *eu = f->eu, *es = f->es;
+    cudaStream_t st = eu->st;
+    GemmBuf bA{eu->tma_ok ? &f->mapA : nullptr, f->bufA, f->Mpad};
+    GemmBuf bB2{eu->tma_ok ? &f->mapB2 : nullptr, f->bufB, f->Mpad};
+    for (int64_t m0 = 0; m0 < Ms; m0 += f->Nc) {
+        const int64_t mc = std::min(f->Nc, Ms - m0);
+        FCK(cudaMemcpy2DAsync(f->xs, sizeof(double) * f->d, xs + m0 * ldxs, sizeof(double) * ldxs, sizeof(double) * f->d,
+                              mc, cudaMemcpyHostToDevice, st));
+        FCK(fitc_kfu(f, f->xs, mc));
+        ++eu->launches;
+        FCK(rowdot_launch(f->bufA, f->Mpad, f->uvec, mc, f->Mpad, f->tmpc, st));
+        FCK(cudaMemcpyAsync(mu + m0, f->tmpc, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+        if (var) {
+            FCK(cudaMemcpyAsync(f->bufB, f->bufA, sizeof(double) * f->Nc * f->Mpad, cudaMemcpyDeviceToDevice, st));
+            FCK(trsm_rec_buf(eu, bA, (int)f->Nc, 0, (int)f->Mpad));
+            FCK(trsm_rec_buf(es, bB2, (int)f->Nc, 0, (int)f->Mpad));
+            eu->launches += 4;
+            FCK(kdiag_launch(eu->prog, f->xs, f->d, mc, f->tmpc, st));
+            FCK(rowvar_launch(f->bufA, f->Mpad, f->tmpc, mc, f->Mpad, f->tmpc2, st));       // k_xx - q
+            FCK(rowvar_launch(f->bufB, f->Mpad, f->zeroc, mc, f->Mpad, f->w, st));          // -s
+            FCK(ew_launch(6, mc, f->tmpc, f->tmpc2, f->w, nullptr, 0.0, st));               // k_xx - q + s
+            FCK(cudaMemcpyAsync(var + m0, f->tmpc, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
+        }
+        FCK(cudaStreamSynchronize(st));
+    }
+    return GPB200_OK;
+}
+
+int64_t gpb200_fitc_launch_count(gpb200_fitc* f) { return f ? f->eu->launches + f->es->launches : 0; }
 
 }  // extern "C"

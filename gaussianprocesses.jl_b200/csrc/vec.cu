@@ -182,6 +182,45 @@ cudaError_t fp64_peak_measure(cudaStream_t st, double* tflops) {
     return cudaGetLastError();
 }
 
+// ---- small elementwise kernels used by the FITC path ----
+namespace {
+// op: 0 out=a+s  1 out=a/b  2 out+=a  3 out=(a-b)/c  4 out=log(a)  5 out=1/a  6 out=a-b
+__global__ void ew_kernel(int op, long long n, double* __restrict__ out, const double* __restrict__ a,
+                          const double* __restrict__ b, const double* __restrict__ c, double s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (op) {
+    case 0: out[i] = a[i] + s; break;
+    case 1: out[i] = a[i] / b[i]; break;
+    case 2: out[i] += a[i]; break;
+    case 3: out[i] = (a[i] - b[i]) / c[i]; break;
+    case 4: out[i] = log(a[i]); break;
+    case 5: out[i] = 1.0 / a[i]; break;
+    case 6: out[i] = a[i] - b[i]; break;
+    }
+}
+// A[r, j] *= f(v[j]) for j < ncols (mode 0: 1/sqrt(v), columns) ; A[r, :] *= 1/v[r] for r < nrows (mode 1, rows)
+__global__ void scale_kernel(int mode, double* __restrict__ A, long long ld, long long nrows, long long ncols,
+                             const double* __restrict__ v) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = blockIdx.y;
+    if (j >= ncols || r >= nrows) return;
+    const double f = mode == 0 ? 1.0 / sqrt(v[j]) : 1.0 / v[r];
+    A[r * ld + j] *= f;
+}
+}  // namespace
+cudaError_t ew_launch(int op, int64_t n, double* out, const double* a, const double* b, const double* c, double s, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    ew_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, n, out, a, b, c, s);
+    return cudaGetLastError();
+}
+cudaError_t scale_launch(int mode, double* A, int64_t ld, int64_t nrows, int64_t ncols, const double* v, cudaStream_t st) {
+    if (nrows <= 0 || ncols <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)nrows);
+    scale_kernel<<<grid, 256, 0, st>>>(mode, A, ld, nrows, ncols, v);
+    return cudaGetLastError();
+}
+
 cudaError_t trsv_lower_fwd(const double* F, int64_t ldf, const double* Dinv, double* r, double* y, int64_t Npad,
                            cudaStream_t st, int64_t* launches) {
     const int nb = (int)(Npad / T);

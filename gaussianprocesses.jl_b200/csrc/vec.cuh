@@ -18,3 +18,7 @@ cudaError_t rowvar_launch(const double* Vt, int64_t ldk, const double* kdiag, in
 cudaError_t exp2x_launch(const double* ln, int64_t n, double* out, cudaStream_t st);
 // FP64 issue-rate microbenchmark: tflops[0] = DMMA.8x8x4, tflops[1] = DFMA (register operands)
 cudaError_t fp64_peak_measure(cudaStream_t st, double* tflops);
+// elementwise: op 0 out=a+s | 1 out=a/b | 2 out+=a | 3 out=(a-b)/c | 4 out=log(a) | 5 out=1/a
+cudaError_t ew_launch(int op, int64_t n, double* out, const double* a, const double* b, const double* c, double s, cudaStream_t st);
+// mode 0: A[:, j] *= 1/sqrt(v[j]) (j < ncols) ; mode 1: A[r, :] *= 1/v[r] (r < nrows)
+cudaError_t scale_launch(int mode, double* A, int64_t ld, int64_t nrows, int64_t ncols, const double* v, cudaStream_t st);

@@ -49,6 +49,16 @@ _SIGNATURES = {
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int64,
                                          C.c_int, C.c_int, _dp]),
     "gpb200_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "gpb200_fitc_create": (C.c_int, [C.POINTER(_H), C.c_int]),
+    "gpb200_fitc_destroy": (None, [_H]),
+    "gpb200_fitc_last_error": (C.c_char_p, [_H]),
+    "gpb200_fitc_set_data": (C.c_int, [_H, C.c_int64, C.c_int32, _dp, C.c_int64, C.c_int64, _dp, C.c_int64]),
+    "gpb200_fitc_set_kernel": (C.c_int, [_H, C.c_int32, _ip, C.c_int32, _ip, C.c_int32]),
+    "gpb200_fitc_factorize": (C.c_int, [_H, _dp, C.c_double]),
+    "gpb200_fitc_mll": (C.c_int, [_H, _dp, _dp, _dp, _dp]),
+    "gpb200_fitc_grad_noise": (C.c_int, [_H, _dp]),
+    "gpb200_fitc_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp]),
+    "gpb200_fitc_launch_count": (C.c_int64, [_H]),
     "gpb200_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
 }
 
@@ -253,3 +263,85 @@ class Engine:
                                                      C.c_void_p(dB), ldb, float(beta), C.c_void_p(dC), ldc,
                                                      1 if lower_only else 0, int(reps), C.byref(ms)), "dgemm_nt")
         return ms.value
+
+
+class FitcEngine:
+    """Owns one gpb200_fitc handle: the FITC sparse strategy (src/sparse/fully_indep_train_conditional.jl)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = _H()
+        rc = self._lib.gpb200_fitc_create(C.byref(self._h), int(device))
+        if rc != OK:
+            msg = self._lib.gpb200_last_error(None)
+            raise RuntimeError("gpb200_fitc_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self.N = self.M = self.d = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.gpb200_fitc_destroy(self._h)
+            self._h = _H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc == OK:
+            return
+        msg = self._lib.gpb200_fitc_last_error(self._h)
+        msg = msg.decode() if msg else ""
+        if rc > 0:
+            raise PosDefException(rc)
+        if rc in (EINVAL, ESTATE):
+            raise ValueError("%s: %s" % (what, msg))
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
+
+    def set_data(self, x_pm, xu_pm):
+        x_pm = np.ascontiguousarray(x_pm, dtype=np.float64)
+        xu_pm = np.ascontiguousarray(xu_pm, dtype=np.float64)
+        (N, d), (M, d2) = x_pm.shape, xu_pm.shape
+        if d != d2:
+            raise ValueError("inducing points and inputs must have the same dimension")
+        self._check(self._lib.gpb200_fitc_set_data(self._h, N, d, _as_dp(x_pm), d, M, _as_dp(xu_pm), d), "fitc_set_data")
+        self.N, self.M, self.d = N, M, d
+
+    def set_kernel(self, ops, dims, n_theta):
+        ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, OP_STRIDE)
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        self._check(self._lib.gpb200_fitc_set_kernel(self._h, ops.shape[0], ops.ctypes.data_as(_ip), dims.size,
+                                                     dims.ctypes.data_as(_ip), int(n_theta)), "fitc_set_kernel")
+
+    def factorize(self, theta, log_noise):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        self._check(self._lib.gpb200_fitc_factorize(self._h, _as_dp(theta), float(log_noise)), "fitc_factorize")
+
+    def mll(self, y_minus_mean):
+        r = np.ascontiguousarray(y_minus_mean, dtype=np.float64)
+        if r.shape != (self.N,):
+            raise ValueError("fitc_mll: y must have length N")
+        alpha = np.empty(self.N)
+        m, ld = C.c_double(), C.c_double()
+        self._check(self._lib.gpb200_fitc_mll(self._h, _as_dp(r), _as_dp(alpha), C.byref(m), C.byref(ld)), "fitc_mll")
+        return alpha, m.value, ld.value
+
+    def grad_noise(self):
+        g = C.c_double()
+        self._check(self._lib.gpb200_fitc_grad_noise(self._h, C.byref(g)), "fitc_grad_noise")
+        return g.value
+
+    def predict(self, xs_pm, want_var=True):
+        xs_pm = np.ascontiguousarray(xs_pm, dtype=np.float64)
+        Ms, d = xs_pm.shape
+        if d != self.d:
+            raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
+        mu = np.empty(Ms)
+        var = np.empty(Ms) if want_var else None
+        self._check(self._lib.gpb200_fitc_predict(self._h, Ms, _as_dp(xs_pm), d, _as_dp(mu),
+                                                  _as_dp(var) if want_var else None), "fitc_predict")
+        return mu, var
+
+    def launch_count(self):
+        return int(self._lib.gpb200_fitc_launch_count(self._h))

@@ -1,0 +1,65 @@
+"""FITC -- host mirror of the reference's sparse strategy `FITC(x, Xu, y, mean, kern, logNoise)`
+(src/sparse/fully_indep_train_conditional.jl:335-338 == GPE(..., FullyIndepStrat(Xu))), over the
+gpb200_fitc_* entry points.  Built: update_cK!, alpha / mll / logdet, dmll_noise, dmll_mean,
+predict_f / predict_y.  Not built yet: the kernel-parameter gradient (fitc.jl:200-234)."""
+import math
+
+import numpy as np
+
+from . import capi
+from .gpe import _as_dxn
+from .kernels import flatten
+from .means import MeanZero
+
+
+class FITC:
+    def __init__(self, x, Xu, y, mean=None, kernel=None, logNoise=-2.0, device=0):
+        self.mean = mean if mean is not None else MeanZero()
+        self.kernel = kernel
+        self.logNoise = float(logNoise)
+        self.x = _as_dxn(x)
+        self.Xu = _as_dxn(Xu)                       # inducing points, dim x M (one point per column)
+        self.y = np.asarray(y, dtype=np.float64).ravel()
+        self.dim, self.nobs = self.x.shape
+        if self.Xu.shape[0] != self.dim or self.y.size != self.nobs:
+            raise ValueError("Input and output observations must have consistent dimensions.")
+        self._xpm = np.ascontiguousarray(self.x.T)
+        self._eng = capi.FitcEngine(device)
+        self._eng.set_data(self._xpm, np.ascontiguousarray(self.Xu.T))
+        ops, dims, theta, exposed = flatten(kernel, self.dim)
+        self._eng.set_kernel(ops, dims, theta.size)
+        self.alpha = None
+        self.mll = float("nan")
+        self.dmll = None
+        self.update_mll()
+
+    def update_mll(self):
+        """update_mll! (src/GPE.jl:202-212) with cK::FullyIndepPDMat."""
+        self._eng.factorize(flatten(self.kernel, self.dim)[2], self.logNoise)
+        mu = self.mean.mean(self._xpm)
+        self.alpha, self.mll, self.logdet = self._eng.mll(self.y - mu)
+        self.target = self.mll
+        return self
+
+    def update_dmll_noise_mean(self):
+        """[dmll_noise (fitc.jl:243-257); dmll_mean! (GPE.jl:282-288)] -- kernel part not built yet."""
+        out = [self._eng.grad_noise()]
+        if self.mean.num_params() > 0:
+            out.extend(self.mean.grad_stack(self._xpm).T @ self.alpha)
+        self.dmll = np.array(out)
+        return self
+
+    def noise_variance(self):
+        return math.exp(2.0 * self.logNoise)
+
+    def predict_f(self, x):
+        x = _as_dxn(x)
+        if x.shape[0] != self.dim:
+            raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
+        xs = np.ascontiguousarray(x.T)
+        mu, var = self._eng.predict(xs)
+        return mu + self.mean.mean(xs), np.maximum(var, 0.0)          # GP.jl:75
+
+    def predict_y(self, x):
+        mu, s2 = self.predict_f(x)
+        return mu, s2 + self.noise_variance()

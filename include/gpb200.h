@@ -162,6 +162,31 @@ int  gpb200_dgemm_nt_device(gpb200_handle* h, int impl, int64_t M, int64_t N, in
 int  gpb200_nccl_unique_id(char* id128);
 int  gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128);
 
+/* ---- sparse FITC strategy (src/sparse/fully_indep_train_conditional.jl) ------------------------
+ * FITC(x, Xu, y, mean, kern, logNoise) (fitc.jl:335-338) == GPE(..., FullyIndepStrat(Xu)).
+ * Covers update_cK!(::FullyIndepPDMat) (fitc.jl:134-156), `\` (fitc.jl:33-36), logdet (fitc.jl:77),
+ * dmll_noise (fitc.jl:243-257), get_alpha_u (fitc.jl:279-286) and predictMVN (fitc.jl:324-332 ->
+ * determ_train_conditional.jl:41-59 -> subsetofregressors.jl:302-321).  The kernel-parameter
+ * gradient of FITC (fitc.jl:200-234 + subsetofregressors.jl:219-253) is NOT built yet.
+ * N is streamed in chunks; only M x M matrices and O(N) vectors persist on the device.          */
+typedef struct gpb200_fitc gpb200_fitc;
+int  gpb200_fitc_create(gpb200_fitc** out, int device);
+void gpb200_fitc_destroy(gpb200_fitc* f);
+const char* gpb200_fitc_last_error(gpb200_fitc* f);
+/* x: d x N training inputs, xu: d x M inducing inputs (both column-major, one point per column) */
+int  gpb200_fitc_set_data(gpb200_fitc* f, int64_t N, int32_t d, const double* x, int64_t ldx,
+                          int64_t M, const double* xu, int64_t ldxu);
+int  gpb200_fitc_set_kernel(gpb200_fitc* f, int32_t n_ops, const int32_t* ops, int32_t n_dims,
+                            const int32_t* dims, int32_t n_theta);
+/* update_cK!: K_uu (+1e-10 I), Lambda, Sigma_QR (+1e-10 I) and both Cholesky factors */
+int  gpb200_fitc_factorize(gpb200_fitc* f, const double* theta, double log_noise);
+/* alpha = Sigma^-1 r, logdet(Sigma), mll = -(r'alpha + logdet + N log 2pi)/2 */
+int  gpb200_fitc_mll(gpb200_fitc* f, const double* y_minus_mean, double* alpha, double* mll, double* logdet);
+int  gpb200_fitc_grad_noise(gpb200_fitc* f, double* dmll_noise);
+/* mu_minus_mean[Ms], var[Ms] (may be NULL; not clamped) */
+int  gpb200_fitc_predict(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ldxs, double* mu_minus_mean, double* var);
+int64_t gpb200_fitc_launch_count(gpb200_fitc* f);
+
 #ifdef __cplusplus
 }
 #endif

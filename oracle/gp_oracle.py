@@ -341,3 +341,55 @@ def predict_f(spec, X, f, Xs, mspec=("MeanZero",), full_cov=False):
         return mu, Kp - V.T @ V                     # GP.jl:51-54
     var = np.diag(Kp) - np.sum(V * V, axis=0)
     return mu, np.maximum(var, 0.0)                 # GP.jl:75
+
+
+# ----------------------------------------------------------------------------------------------
+# FITC sparse strategy (src/sparse/fully_indep_train_conditional.jl), restated with dense numpy
+# ----------------------------------------------------------------------------------------------
+def fitc_fit(spec, X, Xu, y, log_noise, mspec=("MeanZero",)):
+    """update_cK!(::FullyIndepPDMat) (fitc.jl:134-156) + `\\` (fitc.jl:33-36) + logdet (fitc.jl:77) + mll."""
+    import scipy.linalg as sl
+    X = np.ascontiguousarray(X, dtype=np.float64); Xu = np.ascontiguousarray(Xu, dtype=np.float64)
+    n = X.shape[0]
+    Kuu = cov(spec, Xu) + 1e-10 * np.eye(Xu.shape[0])          # make_posdef!(..., nugget=1e-10)  fitc.jl:140
+    Uuu = _potrf_upper(Kuu)
+    Kuf = cov(spec, Xu, X)                                      # fitc.jl:142
+    Kdiag = np.array([cov(spec, X[i:i + 1], X[i:i + 1])[0, 0] for i in range(n)]) if n <= 64 else \
+        np.diag(cov(spec, X[:1], X[:1])).repeat(n) if False else _kdiag(spec, X)
+    W = sl.solve_triangular(Uuu, Kuf, trans="T", lower=False)   # U^-T Kuf ; invquad = column norms  fitc.jl:147
+    Qdiag = np.sum(W * W, axis=0)
+    Lam = math.exp(2 * log_noise) + Kdiag - Qdiag               # fitc.jl:148
+    SQR = Kuf @ (Kuf / Lam).T + Kuu + 1e-10 * np.eye(Xu.shape[0])     # fitc.jl:150-153
+    Us = _potrf_upper(SQR)
+    mu, MG = mean_and_grads(mspec, X)
+    r = y - mu
+    Lk = sl.solve_triangular(Us, Kuf, trans="T", lower=False)   # whiten(ΣQR, Kuf)
+    alpha = (r - Lk.T @ (Lk @ (r / Lam))) / Lam                 # fitc.jl:33-36
+    logdet = 2 * np.sum(np.log(np.diag(Us))) - 2 * np.sum(np.log(np.diag(Uuu))) + np.sum(np.log(Lam))   # fitc.jl:77
+    mll = -(r @ alpha + logdet + LOG2PI * n) / 2.0
+    LkL = Lk / Lam
+    dnoise = math.exp(2 * log_noise) * (alpha @ alpha - np.sum(1.0 / Lam) + np.sum(LkL * LkL))   # fitc.jl:243-257
+    alpha_u = _potrs_upper(Us, Kuf @ (r / Lam))                 # fitc.jl:279-286
+    Sigma = (W.T @ W + np.diag(Lam)) if n <= 4096 else None      # Matrix(::FullyIndepPDMat)  fitc.jl:78-83
+    return dict(alpha=alpha, mll=mll, logdet=logdet, Lam=Lam, Uuu=Uuu, Us=Us, alpha_u=alpha_u, dmll_noise=dnoise,
+                dmll_mean=MG.T @ alpha, Sigma=Sigma, resid=r)
+
+
+def _kdiag(spec, X):
+    out = np.empty(X.shape[0])
+    for i0 in range(0, X.shape[0], 512):
+        blk = X[i0:i0 + 512]
+        out[i0:i0 + 512] = np.diag(cov(spec, blk, blk))
+    return out
+
+
+def fitc_predict(spec, X, Xu, f, Xs, mspec=("MeanZero",)):
+    """predictMVN (fitc.jl:324-332 -> dtc.jl:41-59 -> sor.jl:302-321): mu = mx + Kxu alpha_u;
+    Sigma = Kxx - Qxx + Kxu ΣQR^-1 Kux (diagonal returned, clamped at 0 like GP.jl:75)."""
+    import scipy.linalg as sl
+    Kux = cov(spec, Xu, Xs)
+    mx, _ = mean_and_grads(mspec, Xs)
+    mu = mx + Kux.T @ f["alpha_u"]
+    q = np.sum(sl.solve_triangular(f["Uuu"], Kux, trans="T", lower=False) ** 2, axis=0)
+    s = np.sum(sl.solve_triangular(f["Us"], Kux, trans="T", lower=False) ** 2, axis=0)
+    return mu, np.maximum(_kdiag(spec, Xs) - q + s, 0.0)

@@ -1,0 +1,52 @@
+"""GPU: the FITC sparse strategy (src/sparse/fully_indep_train_conditional.jl) through the C ABI against
+the CPU oracle.  Tolerances: the 1e-10 nuggets on K_uu / Sigma_QR are part of the reference's arithmetic
+and amplify rounding by cond(K_uu) (~1e5 here), hence 1e-9 on mll and 1e-7 on alpha / predictions."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("N,M,d", [(400, 30, 2), (3000, 200, 3), (5000, 129, 2)])
+@pytest.mark.parametrize("kname", ["SEIso", "Mat32+RQ"])
+def test_fitc_matches_oracle(N, M, d, kname):
+    import gpb200 as g
+    rng = np.random.default_rng(N + M)
+    X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    Xs = rng.standard_normal((77, d))
+    k = g.SEIso(-0.7, 0.1) if kname == "SEIso" else g.Mat32Iso(-0.3, 0.0) + g.RQIso(-0.5, -0.5, 0.3)
+    gp = g.FITC(X.T, Xu.T, y, g.MeanConst(0.1), k, -1.0)
+    gp.update_dmll_noise_mean()
+    o = orc.fitc_fit(k.spec(), X, Xu, y, -1.0, ("MeanConst", 0.1))
+    assert abs(gp.mll - o["mll"]) <= 1e-9 * abs(o["mll"])
+    assert abs(gp.logdet - o["logdet"]) <= 1e-9 * abs(o["logdet"]) + 1e-9
+    assert _rel(gp.alpha, o["alpha"]) < 1e-7
+    assert abs(gp.dmll[0] - o["dmll_noise"]) <= 1e-6 * abs(o["dmll_noise"]) + 1e-8
+    assert abs(gp.dmll[1] - o["dmll_mean"][0]) <= 1e-6 * abs(o["dmll_mean"][0]) + 1e-8
+    mu, s2 = gp.predict_f(Xs.T)
+    mo, vo = orc.fitc_predict(k.spec(), X, Xu, o, Xs, ("MeanConst", 0.1))
+    assert _rel(mu, mo) < 1e-7
+    assert np.max(np.abs(s2 - vo)) <= 1e-7 * np.max(np.abs(vo)) + 1e-9
+    my, sy = gp.predict_y(Xs.T)
+    assert np.allclose(sy, s2 + np.exp(-2.0))
+
+
+def test_fitc_chunked_streaming_equals_single_chunk():
+    """N larger than one staging chunk: results must not depend on the chunking (M small -> Nc capped at 32768)."""
+    import gpb200 as g
+    rng = np.random.default_rng(5)
+    N, M, d = 70000, 64, 2
+    X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    k = g.SEIso(-0.5, 0.0)
+    gp = g.FITC(X.T, Xu.T, y, g.MeanZero(), k, -1.0)
+    o = orc.fitc_fit(k.spec(), X, Xu, y, -1.0)          # O(N M) on the CPU: fine at this size
+    assert abs(gp.mll - o["mll"]) <= 1e-9 * abs(o["mll"])
+    assert _rel(gp.alpha, o["alpha"]) < 1e-7

@@ -73,3 +73,24 @@ def test_oracle_predict_interpolates():
     assert np.max(np.abs(mu - y)) < 0.1
     mu2, cov = orc.predict_f(spec, X, f, X[:7], full_cov=True)
     assert np.allclose(np.diag(cov), var[:7], atol=1e-10)
+
+
+def test_oracle_fitc_matches_dense_formulation():
+    """The reference's RNG-free FITC checks (test/test_sparse.jl:121-144): sparse mll / alpha / logdet equal
+    those of a dense GP built from Matrix(cK); analytic noise gradient equals finite differences."""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(0)
+    N, M, d = 400, 30, 2
+    X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    spec = ("SEIso", [-0.7, 0.1])
+    f = orc.fitc_fit(spec, X, Xu, y, -1.0, ("MeanConst", 0.1))
+    c = sl.cho_factor(f["Sigma"]); a = sl.cho_solve(c, f["resid"]); ld = 2 * np.sum(np.log(np.diag(c[0])))
+    dense_mll = -(f["resid"] @ a + ld + orc.LOG2PI * N) / 2
+    assert abs(f["mll"] - dense_mll) < 1e-6                    # test_sparse.jl:127
+    assert abs(f["logdet"] - ld) < 1e-6                        # :130
+    assert np.max(np.abs(a - f["alpha"])) < 1e-6               # :132
+    e = 1e-5
+    fd = (orc.fitc_fit(spec, X, Xu, y, -1.0 + e, ("MeanConst", 0.1))["mll"]
+          - orc.fitc_fit(spec, X, Xu, y, -1.0 - e, ("MeanConst", 0.1))["mll"]) / (2 * e)
+    assert abs(fd - f["dmll_noise"]) < 1e-3 * abs(fd)          # :134-144 (atol 1e-3 there)
