@@ -13,7 +13,7 @@ def _rel(a, b):
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
 
 
-@pytest.mark.parametrize("N,M,d", [(400, 30, 2), (3000, 200, 3), (5000, 129, 2)])
+@pytest.mark.parametrize("N,M,d", [(400, 30, 2), (3000, 200, 3), (5000, 129, 3)])
 @pytest.mark.parametrize("kname", ["SEIso", "Mat32+RQ"])
 def test_fitc_matches_oracle(N, M, d, kname):
     import gpb200 as g
@@ -42,7 +42,7 @@ def test_fitc_chunked_streaming_equals_single_chunk():
     """N larger than one staging chunk: results must not depend on the chunking (M small -> Nc capped at 32768)."""
     import gpb200 as g
     rng = np.random.default_rng(5)
-    N, M, d = 70000, 64, 2
+    N, M, d = 70000, 64, 3
     X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
     Xu = X[rng.permutation(N)[:M]]
     k = g.SEIso(-0.5, 0.0)
