@@ -112,6 +112,11 @@ struct gpb200_fitc {
     double *bvec = nullptr, *uvec = nullptr, *tmpm = nullptr, *rhsm = nullptr, *scal = nullptr;   // Mpad
     double *bufA = nullptr, *bufB = nullptr;   // Nc x Mpad (K_fu chunk) ; Mpad x Nc (K_uf chunk)
     CUtensorMap mapA{}, mapB{}, mapB2{};
+    // kernel-gradient workspace (allocated on first use)
+    double *bufC = nullptr, *Hbuf = nullptr, *Wbuf = nullptr, *Tbuf = nullptr, *gvec = nullptr, *betav = nullptr;
+    double *gpart = nullptr, *gacc = nullptr, *gtmp = nullptr;
+    CUtensorMap mapAt{}, mapC{}, mapCt{}, mapH{}, mapT{};
+    bool grad_ws = false;
     double noise_var = 0.0;
     bool has_data = false, has_kernel = false, factored = false, alpha_ready = false;
     std::string err;
@@ -1274,7 +1279,8 @@ void gpb200_fitc_destroy(gpb200_fitc* f) {
     cudaSetDevice(f->device);
     if (f->eu && f->eu->st) cudaStreamSynchronize(f->eu->st);
     double** ptrs[] = {&f->x, &f->xs, &f->lam, &f->y, &f->alpha, &f->tmpn, &f->w, &f->tmpc, &f->zeroc, &f->tmpc2,
-                       &f->bvec, &f->uvec, &f->tmpm, &f->rhsm, &f->scal, &f->bufA, &f->bufB};
+                       &f->bvec, &f->uvec, &f->tmpm, &f->rhsm, &f->scal, &f->bufA, &f->bufB,
+                       &f->bufC, &f->Hbuf, &f->Wbuf, &f->Tbuf, &f->gvec, &f->betav, &f->gpart, &f->gacc, &f->gtmp};
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (f->es) { f->es->st = nullptr; f->es->own_stream = false; gpb200_destroy(f->es); }
     if (f->eu) gpb200_destroy(f->eu);
@@ -1307,8 +1313,10 @@ int gpb200_fitc_set_data(gpb200_fitc* f, int64_t N, int32_t d, const double* x, 
     FSUB(gpb200_set_data(f->es, M, d, xu, ldxu), f->es);
     cudaStream_t st = f->eu->st;
     double** ptrs[] = {&f->x, &f->xs, &f->lam, &f->y, &f->alpha, &f->tmpn, &f->w, &f->tmpc, &f->zeroc, &f->tmpc2,
-                       &f->bvec, &f->uvec, &f->tmpm, &f->rhsm, &f->scal, &f->bufA, &f->bufB};
+                       &f->bvec, &f->uvec, &f->tmpm, &f->rhsm, &f->scal, &f->bufA, &f->bufB,
+                       &f->bufC, &f->Hbuf, &f->Wbuf, &f->Tbuf, &f->gvec, &f->betav, &f->gpart, &f->gacc, &f->gtmp};
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    f->grad_ws = false;
     f->N = N; f->M = M; f->d = d; f->Mpad = f->eu->Npad;
     // chunk of data rows: two staging buffers of ~2 GB each at most
     int64_t nc = (int64_t)(2.0e9 / (8.0 * (double)f->Mpad)) / TILE * TILE;
@@ -1513,6 +1521,131 @@ int gpb200_fitc_predict(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ld
         }
         FCK(cudaStreamSynchronize(st));
     }
+    return GPB200_OK;
+}
+
+
+// Kernel-parameter gradient of the FITC mll: dmll_kern!(::FullyIndepStrat) (fitc.jl:200-234) on top of
+// dmll_kern!(::SubsetOfRegsStrategy) (subsetofregressors.jl:219-253), regrouped so that every
+// parameter shares the same three weighted traces (kernel derivatives recomputed on the fly):
+//   dmll_p = 1/2 [ <W_fu, dK_fu/dθ_p> + <W_uu, dK_uu/dθ_p> + sum_i g_i dK_ii/dθ_p ]
+//   g_i   = alpha_i^2 - (Sigma^-1)_ii ,  (Sigma^-1)_ii = 1/L_i - K_fu,i S^-1 K_uf,i / L_i^2      (trinvAB, fitc.jl:63-67)
+//   W_fu  = 2 alpha beta' - 2 L^-1 K_fu S^-1 - 2 diag(g) K_fu K_uu^-1 ,  beta = K_uu^-1 K_uf alpha   (sor.jl:147)
+//   W_uu  = -beta beta' + K_uu^-1 - S^-1 + K_uu^-1 (K_uf diag(g) K_fu) K_uu^-1
+// with S = Sigma_QR, L = Lambda; uses Sigma^-1 K_fu K_uu^-1 = L^-1 K_fu S^-1 and
+// K_uu^-1 K_uf Sigma^-1 K_fu K_uu^-1 = K_uu^-1 - S^-1 (both follow from S = K_uu + K_uf L^-1 K_fu).
+// All O(M^2 N) work is NT GEMMs against the explicit M x M inverses (grad_prepare of the sub-engines).
+int gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel) {
+    if (!f || !dmll_kernel) return GPB200_EINVAL;
+    if (!f->factored || !f->alpha_ready) { f->err = "fitc_grad_kernel: factorize and mll first"; return GPB200_ESTATE; }
+    FCK(cudaSetDevice(f->device));
+    gpb200_handle *eu = f->eu, *es = f->es;
+    cudaStream_t st = eu->st;
+    const int np = eu->prog.n_theta;
+    const int64_t Mp = f->Mpad, Nc = f->Nc;
+    if (!f->grad_ws) {
+        FCK(cudaMalloc(&f->bufC, sizeof(double) * Nc * Mp));
+        for (double** p : {&f->Hbuf, &f->Wbuf, &f->Tbuf}) FCK(cudaMalloc(p, sizeof(double) * Mp * Mp));
+        FCK(cudaMalloc(&f->gvec, sizeof(double) * (f->N + TILE)));
+        FCK(cudaMalloc(&f->betav, sizeof(double) * Mp));
+        const size_t tiles = (size_t)std::max((Nc / TILE) * (Mp / TILE), (Mp / TILE) * (Mp / TILE));
+        FCK(cudaMalloc(&f->gpart, sizeof(double) * tiles * GPB200_MAX_THETA));
+        FCK(cudaMalloc(&f->gacc, sizeof(double) * GPB200_MAX_THETA));
+        FCK(cudaMalloc(&f->gtmp, sizeof(double) * GPB200_MAX_THETA));
+        if (eu->tma_ok) {
+            const bool ok = gemm_make_tensor_map(&f->mapAt, f->bufA, Mp, Nc, Nc) && gemm_make_tensor_map(&f->mapC, f->bufC, Nc, Mp, Mp) &&
+                            gemm_make_tensor_map(&f->mapCt, f->bufC, Mp, Nc, Nc) && gemm_make_tensor_map(&f->mapH, f->Hbuf, Mp, Mp, Mp) &&
+                            gemm_make_tensor_map(&f->mapT, f->Tbuf, Mp, Mp, Mp);
+            if (!ok) { f->err = "fitc_grad_kernel: cuTensorMapEncodeTiled failed"; return GPB200_ECUDA; }
+        }
+        f->grad_ws = true;
+    }
+    // explicit K_uu^-1 and Sigma_QR^-1 (full symmetric) in the sub-engines' G buffers
+    FSUB(gpb200_grad_prepare(eu), eu);
+    FSUB(gpb200_grad_prepare(es), es);
+    eu->launches += 2;
+    FCK(symmetrize_launch(eu->G, eu->ld, Mp, st));
+    FCK(symmetrize_launch(es->G, es->ld, Mp, st));
+    const bool tma = eu->tma_ok;
+    GemmBuf bA{tma ? &f->mapA : nullptr, f->bufA, Mp}, bAt{tma ? &f->mapAt : nullptr, f->bufA, Nc};
+    GemmBuf bCt{tma ? &f->mapCt : nullptr, f->bufC, Nc};
+    GemmBuf bH{tma ? &f->mapH : nullptr, f->Hbuf, Mp}, bT{tma ? &f->mapT : nullptr, f->Tbuf, Mp};
+    // beta = K_uu^-1 (K_uf alpha)
+    FCK(cudaMemsetAsync(f->rhsm, 0, sizeof(double) * Mp, st));
+    for (int64_t r0 = 0; r0 < f->N; r0 += Nc) {
+        const int64_t nc = std::min(Nc, f->N - r0);
+        FCK(fitc_kuf(f, f->x + r0 * f->d, nc));
+        eu->launches += 2;
+        FCK(cudaMemsetAsync(f->w, 0, sizeof(double) * Nc, st));
+        FCK(cudaMemcpyAsync(f->w, f->alpha + r0, sizeof(double) * nc, cudaMemcpyDeviceToDevice, st));
+        FCK(rowdot_launch(f->bufB, Nc, f->w, f->M, Nc, f->tmpm, st));
+        FCK(ew_launch(2, f->M, f->rhsm, f->tmpm, nullptr, nullptr, 0.0, st));
+    }
+    FCK(solve_device(eu, f->rhsm, f->tmpm, f->betav));
+    FCK(cudaMemsetAsync(f->gacc, 0, sizeof(double) * GPB200_MAX_THETA, st));
+    FCK(cudaMemsetAsync(f->Hbuf, 0, sizeof(double) * Mp * Mp, st));
+    for (int64_t r0 = 0; r0 < f->N; r0 += Nc) {
+        const int64_t nc = std::min(Nc, f->N - r0);
+        const double* xr = f->x + r0 * f->d;
+        FCK(fitc_kfu(f, xr, nc));                                         // bufA = K_fu chunk
+        {   // P2 = K_fu S^-1 -> bufB (as Nc x Mpad)
+            GemmDesc g = gemm_desc_default();
+            g.A = GemmOperand{bA, bufNone(), 0, 0};
+            g.B = GemmOperand{bufG(es), bufNone(), 0, 0};
+            g.C = f->bufB; g.ldc = Mp; g.M = (int)Nc; g.N = (int)Mp; g.K = (int)Mp;
+            FCK(launch_gemm(es, g));
+        }
+        eu->launches += 2;
+        FCK(rowdot2_launch(f->bufA, f->bufB, Mp, nc, Mp, f->tmpc, st));
+        FCK(fitc_g_launch(nc, f->alpha + r0, f->lam + r0, f->tmpc, f->gvec + r0, st));
+        {   // P1 = K_fu K_uu^-1 -> bufC
+            GemmDesc g = gemm_desc_default();
+            g.A = GemmOperand{bA, bufNone(), 0, 0};
+            g.B = GemmOperand{bufG(eu), bufNone(), 0, 0};
+            g.C = f->bufC; g.ldc = Mp; g.M = (int)Nc; g.N = (int)Mp; g.K = (int)Mp;
+            FCK(launch_gemm(eu, g));
+        }
+        eu->launches += 4;
+        FCK(fitc_wfu_launch(f->bufB, f->bufC, Mp, nc, f->M, f->alpha + r0, f->lam + r0, f->gvec + r0, f->betav, st));
+        FCK(trace_rect_launch(eu->prog, xr, f->d, nc, eu->x, f->d, f->M, f->d, f->bufB, Mp, f->gpart, f->gtmp, st));
+        FCK(ew_launch(2, np, f->gacc, f->gtmp, nullptr, nullptr, 0.0, st));
+        // diagonal term sum_i g_i dK_ii/dθ_p (scratch: bufC as np x nc)
+        FCK(kdiag_grad_launch(eu->prog, xr, f->d, nc, f->gvec + r0, f->bufC, st));
+        for (int p = 0; p < np; ++p) { ++eu->launches; FCK(sum_launch(f->bufC + (size_t)p * nc, nc, f->gtmp + p, st)); }
+        FCK(ew_launch(2, np, f->gacc, f->gtmp, nullptr, nullptr, 0.0, st));
+        // H += K_uf diag(g) K_fu
+        ++eu->launches;
+        FCK(crossgram_launch(eu->prog, eu->x, f->d, f->M, Mp, xr, f->d, nc, Nc, f->d, f->bufA, Nc, st));   // bufA = K_uf chunk (Mpad x Nc)
+        FCK(cudaMemcpyAsync(f->bufC, f->bufA, sizeof(double) * Mp * Nc, cudaMemcpyDeviceToDevice, st));
+        ++eu->launches;
+        FCK(colscale_launch(f->bufC, Nc, Mp, nc, f->gvec + r0, st));
+        {
+            GemmDesc g = gemm_desc_default();
+            g.A = GemmOperand{bAt, bufNone(), 0, 0};
+            g.B = GemmOperand{bCt, bufNone(), 0, 0};
+            g.C = f->Hbuf; g.ldc = Mp; g.M = (int)Mp; g.N = (int)Mp; g.K = (int)Nc;
+            g.alpha = 1.0; g.beta = 1.0;
+            FCK(launch_gemm(eu, g));
+        }
+    }
+    {   // T = K_uu^-1 H ; Wbuf = K_uu^-1 T' = K_uu^-1 H K_uu^-1
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bufG(eu), bufNone(), 0, 0};
+        g.B = GemmOperand{bH, bufNone(), 0, 0};
+        g.C = f->Tbuf; g.ldc = Mp; g.M = (int)Mp; g.N = (int)Mp; g.K = (int)Mp;
+        FCK(launch_gemm(eu, g));
+        g.B = GemmOperand{bT, bufNone(), 0, 0};
+        g.C = f->Wbuf;
+        FCK(launch_gemm(eu, g));
+    }
+    eu->launches += 4;
+    FCK(fitc_wuu_launch(f->Wbuf, f->Wbuf, eu->G, es->G, Mp, f->M, f->betav, st));
+    FCK(trace_rect_launch(eu->prog, eu->x, f->d, f->M, eu->x, f->d, f->M, f->d, f->Wbuf, Mp, f->gpart, f->gtmp, st));
+    FCK(ew_launch(2, np, f->gacc, f->gtmp, nullptr, nullptr, 0.0, st));
+    std::vector<double> out((size_t)std::max(np, 1));
+    FCK(cudaMemcpyAsync(out.data(), f->gacc, sizeof(double) * np, cudaMemcpyDeviceToHost, st));
+    FCK(cudaStreamSynchronize(st));
+    for (int p = 0; p < np; ++p) dmll_kernel[p] = 0.5 * out[p];
     return GPB200_OK;
 }
 

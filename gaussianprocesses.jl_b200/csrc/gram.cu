@@ -304,6 +304,90 @@ __global__ void reduce_partials_kernel(const double* __restrict__ part, int tile
     if (threadIdx.x == 0) out[p] = s[0];
 }
 
+// ------------------------------------------------------------------------------------------
+// rectangular weighted trace (FITC gradient): part[tile][p] = sum_{i,m in tile} W[i,m] dk(x1_i, x2_m)/dθ_p
+// ------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(NT) trace_rect_kernel(const __grid_constant__ KProg P, const double* __restrict__ x1,
+                                                        long long ldx1, long long N1, const double* __restrict__ x2,
+                                                        long long ldx2, long long N2, int d,
+                                                        const double* __restrict__ W, long long ldw,
+                                                        double* __restrict__ part) {
+    const int bm = blockIdx.y, bn = blockIdx.x;
+    const int np = P.n_theta;
+    extern __shared__ double sm[];
+    const int ds = d | 1;
+    double* sXi = sm;
+    double* sXj = sXi + TB * ds;
+    double* sRed = sXj + TB * ds;
+    load_xtile(sXi, x1, ldx1, d, ds, (long long)bm * TB, N1);
+    load_xtile(sXj, x2, ldx2, d, ds, (long long)bn * TB, N2);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[FAST ? 2 : GPB200_MAX_THETA];
+    const int nacc = FAST ? 2 : np;
+    for (int p = 0; p < nacc; ++p) acc[p] = 0.0;
+    double gbuf[FAST ? 1 : GPB200_MAX_THETA];
+    double il2 = 0.0, mh = 0.0, s2 = 0.0;
+    if (FAST) { il2 = 1.0 / P.par[0]; mh = -0.5 / P.par[0]; s2 = P.par[1]; }
+#pragma unroll 1
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp * 16 + rr;
+        const long long gi = (long long)bm * TB + r;
+        if (gi >= N1) continue;
+        const double* xi = sXi + r * ds;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int c0 = b * 64 + lane * 2;
+            const long long gj0 = (long long)bn * TB + c0;
+            if (gj0 >= N2) continue;
+            const double2 wv = *reinterpret_cast<const double2*>(W + gi * ldw + gj0);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long long gj = gj0 + e;
+                if (gj >= N2) continue;
+                const double w = e ? wv.y : wv.x;
+                const double* xj = sXj + (c0 + e) * ds;
+                if (FAST) {
+                    double r2 = 0.0;
+                    for (int k = 0; k < d; ++k) { const double df = xi[k] - xj[k]; r2 += df * df; }
+                    const double kv = s2 * exp(mh * r2);
+                    acc[0] += w * (r2 * il2 * kv);
+                    acc[1] += w * (2.0 * kv);
+                } else {
+                    kprog_eval<true>(P, xi, xj, gbuf);
+                    for (int p = 0; p < np; ++p) acc[p] += w * gbuf[p];
+                }
+            }
+        }
+    }
+    for (int p = 0; p < nacc; ++p) {
+        double v = acc[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sRed[warp * nacc + p] = v;
+    }
+    __syncthreads();
+    const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    for (int p = threadIdx.x; p < nacc; p += NT) {
+        double v = 0.0;
+        for (int w8 = 0; w8 < NT / 32; ++w8) v += sRed[w8 * nacc + p];
+        part[lin * nacc + p] = v;
+    }
+}
+
+// out[i*np + p] = g[i] * dk(x_i, x_i)/dθ_p     (diagonal term of the FITC gradient)
+__global__ void kdiag_grad_kernel(const __grid_constant__ KProg P, const double* __restrict__ x, long long ldx,
+                                  long long N, const double* __restrict__ gvec, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double gbuf[GPB200_MAX_THETA];
+    const double* xi = x + i * ldx;
+    kprog_eval<true>(P, xi, xi, gbuf);
+    const double gi = gvec[i];
+    for (int p = 0; p < P.n_theta; ++p) out[(long long)p * N + i] = gi * gbuf[p];
+}
+
 size_t xtile_smem(int d) { return (size_t)2 * TB * (d | 1) * sizeof(double); }
 
 template <typename K>
@@ -385,5 +469,31 @@ cudaError_t trace_launch(const KProg& P, const double* x, int64_t ldx, int d, in
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     reduce_partials_kernel<<<nacc, 256, 0, st>>>(part, tiles, nacc, out);
+    return cudaGetLastError();
+}
+
+// acc_out[p] += sum over the N1 x N2 rectangle of W[i,m] dk(x1_i,x2_m)/dθ_p ; part: [tiles][n_theta] scratch
+cudaError_t trace_rect_launch(const KProg& P, const double* x1, int64_t ldx1, int64_t N1, const double* x2, int64_t ldx2,
+                              int64_t N2, int d, const double* W, int64_t ldw, double* part, double* tmp_out,
+                              cudaStream_t st) {
+    const int tm = (int)((N1 + TB - 1) / TB), tn = (int)((N2 + TB - 1) / TB);
+    const int nacc = P.fast ? 2 : P.n_theta;
+    const size_t sm = xtile_smem(d) + (size_t)(8 * nacc) * sizeof(double);
+    dim3 grid(tn, tm);
+    cudaError_t e;
+    if (P.fast) {
+        if ((e = ensure_smem(trace_rect_kernel<true>, sm)) != cudaSuccess) return e;
+        trace_rect_kernel<true><<<grid, NT, sm, st>>>(P, x1, ldx1, N1, x2, ldx2, N2, d, W, ldw, part);
+    } else {
+        if ((e = ensure_smem(trace_rect_kernel<false>, sm)) != cudaSuccess) return e;
+        trace_rect_kernel<false><<<grid, NT, sm, st>>>(P, x1, ldx1, N1, x2, ldx2, N2, d, W, ldw, part);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    reduce_partials_kernel<<<nacc, 256, 0, st>>>(part, tm * tn, nacc, tmp_out);
+    return cudaGetLastError();
+}
+cudaError_t kdiag_grad_launch(const KProg& P, const double* x, int64_t ldx, int64_t N, const double* gvec, double* out,
+                              cudaStream_t st) {
+    kdiag_grad_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(P, x, ldx, N, gvec, out);
     return cudaGetLastError();
 }

@@ -21,3 +21,10 @@ int trace_num_acc(const KProg& P);
 cudaError_t trace_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad,
                          const double* alpha, const double* Kinv, int64_t ldg, double* part, double* out,
                          cudaStream_t st, int bm_mod = 1, int bm_rem = 0);
+// FITC gradient pieces: rectangular weighted trace (tmp_out[p] = sum W .* dK/dθ_p over the rectangle; part must hold
+// ceil(N1/128)*ceil(N2/128)*n_theta doubles) and g_i * dk(x_i,x_i)/dθ_p written as out[p*N + i]
+cudaError_t trace_rect_launch(const KProg& P, const double* x1, int64_t ldx1, int64_t N1, const double* x2, int64_t ldx2,
+                              int64_t N2, int d, const double* W, int64_t ldw, double* part, double* tmp_out,
+                              cudaStream_t st);
+cudaError_t kdiag_grad_launch(const KProg& P, const double* x, int64_t ldx, int64_t N, const double* gvec, double* out,
+                              cudaStream_t st);

@@ -209,6 +209,88 @@ __global__ void scale_kernel(int mode, double* __restrict__ A, long long ld, lon
     A[r * ld + j] *= f;
 }
 }  // namespace
+namespace {
+// q[r] = sum_c A[r,c] * B[r,c]
+__global__ void __launch_bounds__(256) rowdot2_kernel(const double* __restrict__ A, const double* __restrict__ B, long long ld,
+                                                      long long ncols, double* __restrict__ q) {
+    __shared__ double s[256];
+    const double* ra = A + (long long)blockIdx.x * ld;
+    const double* rb = B + (long long)blockIdx.x * ld;
+    double v = 0.0;
+    for (long long c = threadIdx.x; c < ncols; c += 256) v += ra[c] * rb[c];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) q[blockIdx.x] = s[0];
+}
+// g[i] = alpha_i^2 - (1/lam_i - q_i/lam_i^2)
+__global__ void fitc_g_kernel(long long n, const double* __restrict__ alpha, const double* __restrict__ lam,
+                              const double* __restrict__ q, double* __restrict__ g) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double il = 1.0 / lam[i]; g[i] = alpha[i] * alpha[i] - (il - q[i] * il * il); }
+}
+// P2[i,m] <- 2 alpha_i beta_m - (2/lam_i) P2[i,m] - 2 g_i P1[i,m]      (W_fu, in place on P2)
+__global__ void fitc_wfu_kernel(double* __restrict__ P2, const double* __restrict__ P1, long long ld, long long nrows,
+                                long long ncols, const double* __restrict__ alpha, const double* __restrict__ lam,
+                                const double* __restrict__ g, const double* __restrict__ beta) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (m >= ncols || i >= nrows) return;
+    const long long o = i * ld + m;
+    P2[o] = 2.0 * alpha[i] * beta[m] - (2.0 / lam[i]) * P2[o] - 2.0 * g[i] * P1[o];
+}
+// A[r, j] *= v[j] (j < ncols)
+__global__ void colscale_kernel(double* __restrict__ A, long long ld, long long nrows, long long ncols, const double* __restrict__ v) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = blockIdx.y;
+    if (j < ncols && r < nrows) A[r * ld + j] *= v[j];
+}
+// mirror the lower triangle of an n x n matrix into its upper triangle
+__global__ void symmetrize_kernel(double* __restrict__ A, long long ld, long long n) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (i < n && j < n && j > i) A[i * ld + j] = A[j * ld + i];
+}
+// Wuu[m,n] = T[m,n] - beta_m beta_n + Kinv[m,n] - Sinv[m,n]
+__global__ void fitc_wuu_kernel(double* __restrict__ Wuu, const double* __restrict__ T, const double* __restrict__ Kinv,
+                                const double* __restrict__ Sinv, long long ld, long long n, const double* __restrict__ beta) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (i < n && j < n) Wuu[i * ld + j] = T[i * ld + j] - beta[i] * beta[j] + Kinv[i * ld + j] - Sinv[i * ld + j];
+}
+}  // namespace
+cudaError_t rowdot2_launch(const double* A, const double* B, int64_t ld, int64_t nrows, int64_t ncols, double* q, cudaStream_t st) {
+    if (nrows <= 0) return cudaSuccess;
+    rowdot2_kernel<<<(unsigned)nrows, 256, 0, st>>>(A, B, ld, ncols, q);
+    return cudaGetLastError();
+}
+cudaError_t fitc_g_launch(int64_t n, const double* alpha, const double* lam, const double* q, double* g, cudaStream_t st) {
+    fitc_g_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, alpha, lam, q, g);
+    return cudaGetLastError();
+}
+cudaError_t fitc_wfu_launch(double* P2, const double* P1, int64_t ld, int64_t nrows, int64_t ncols, const double* alpha,
+                            const double* lam, const double* g, const double* beta, cudaStream_t st) {
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)nrows);
+    fitc_wfu_kernel<<<grid, 256, 0, st>>>(P2, P1, ld, nrows, ncols, alpha, lam, g, beta);
+    return cudaGetLastError();
+}
+cudaError_t colscale_launch(double* A, int64_t ld, int64_t nrows, int64_t ncols, const double* v, cudaStream_t st) {
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)nrows);
+    colscale_kernel<<<grid, 256, 0, st>>>(A, ld, nrows, ncols, v);
+    return cudaGetLastError();
+}
+cudaError_t symmetrize_launch(double* A, int64_t ld, int64_t n, cudaStream_t st) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    symmetrize_kernel<<<grid, 256, 0, st>>>(A, ld, n);
+    return cudaGetLastError();
+}
+cudaError_t fitc_wuu_launch(double* Wuu, const double* T, const double* Kinv, const double* Sinv, int64_t ld, int64_t n,
+                            const double* beta, cudaStream_t st) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    fitc_wuu_kernel<<<grid, 256, 0, st>>>(Wuu, T, Kinv, Sinv, ld, n, beta);
+    return cudaGetLastError();
+}
+
 cudaError_t ew_launch(int op, int64_t n, double* out, const double* a, const double* b, const double* c, double s, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     ew_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, n, out, a, b, c, s);

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "gpb200_fitc_factorize": (C.c_int, [_H, _dp, C.c_double]),
     "gpb200_fitc_mll": (C.c_int, [_H, _dp, _dp, _dp, _dp]),
     "gpb200_fitc_grad_noise": (C.c_int, [_H, _dp]),
+    "gpb200_fitc_grad_kernel": (C.c_int, [_H, _dp]),
     "gpb200_fitc_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp]),
     "gpb200_fitc_launch_count": (C.c_int64, [_H]),
     "gpb200_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
@@ -308,7 +309,13 @@ class FitcEngine:
         self._check(self._lib.gpb200_fitc_set_data(self._h, N, d, _as_dp(x_pm), d, M, _as_dp(xu_pm), d), "fitc_set_data")
         self.N, self.M, self.d = N, M, d
 
+    def grad_kernel(self):
+        g = np.empty(max(self.n_theta, 1))
+        self._check(self._lib.gpb200_fitc_grad_kernel(self._h, _as_dp(g)), "fitc_grad_kernel")
+        return g[:self.n_theta].copy()
+
     def set_kernel(self, ops, dims, n_theta):
+        self.n_theta = int(n_theta)
         ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, OP_STRIDE)
         dims = np.ascontiguousarray(dims, dtype=np.int32)
         self._check(self._lib.gpb200_fitc_set_kernel(self._h, ops.shape[0], ops.ctypes.data_as(_ip), dims.size,

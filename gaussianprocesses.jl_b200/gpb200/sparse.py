@@ -1,7 +1,7 @@
 """FITC -- host mirror of the reference's sparse strategy `FITC(x, Xu, y, mean, kern, logNoise)`
 (src/sparse/fully_indep_train_conditional.jl:335-338 == GPE(..., FullyIndepStrat(Xu))), over the
-gpb200_fitc_* entry points.  Built: update_cK!, alpha / mll / logdet, dmll_noise, dmll_mean,
-predict_f / predict_y.  Not built yet: the kernel-parameter gradient (fitc.jl:200-234)."""
+gpb200_fitc_* entry points: update_cK!, alpha / mll / logdet, dmll_noise, dmll_mean!, dmll_kern!,
+predict_f / predict_y."""
 import math
 
 import numpy as np
@@ -27,6 +27,7 @@ class FITC:
         self._eng = capi.FitcEngine(device)
         self._eng.set_data(self._xpm, np.ascontiguousarray(self.Xu.T))
         ops, dims, theta, exposed = flatten(kernel, self.dim)
+        self._exposed = exposed
         self._eng.set_kernel(ops, dims, theta.size)
         self.alpha = None
         self.mll = float("nan")
@@ -48,6 +49,22 @@ class FITC:
             out.extend(self.mean.grad_stack(self._xpm).T @ self.alpha)
         self.dmll = np.array(out)
         return self
+
+    def update_dmll(self, noise=True, domean=True, kern=True):
+        """update_dmll! (src/GPE.jl:298-324) with the FITC strategy: [noise; mean; kernel]."""
+        out = []
+        if noise:
+            out.append(self._eng.grad_noise())                                   # fitc.jl:243-257
+        if domean and self.mean.num_params() > 0:
+            out.extend(self.mean.grad_stack(self._xpm).T @ self.alpha)           # GPE.jl:282-288
+        if kern:
+            out.extend(self._eng.grad_kernel()[self._exposed])                   # fitc.jl:200-234 + sor.jl:219-253
+        self.dmll = np.array(out)
+        return self
+
+    def update_mll_and_dmll(self, **kw):
+        self.update_mll()
+        return self.update_dmll(**kw)
 
     def noise_variance(self):
         return math.exp(2.0 * self.logNoise)

@@ -166,8 +166,8 @@ int  gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128)
  * FITC(x, Xu, y, mean, kern, logNoise) (fitc.jl:335-338) == GPE(..., FullyIndepStrat(Xu)).
  * Covers update_cK!(::FullyIndepPDMat) (fitc.jl:134-156), `\` (fitc.jl:33-36), logdet (fitc.jl:77),
  * dmll_noise (fitc.jl:243-257), get_alpha_u (fitc.jl:279-286) and predictMVN (fitc.jl:324-332 ->
- * determ_train_conditional.jl:41-59 -> subsetofregressors.jl:302-321).  The kernel-parameter
- * gradient of FITC (fitc.jl:200-234 + subsetofregressors.jl:219-253) is NOT built yet.
+ * determ_train_conditional.jl:41-59 -> subsetofregressors.jl:302-321) and the kernel-parameter
+ * gradient dmll_kern! (fitc.jl:200-234 on top of subsetofregressors.jl:140-151, 219-253).
  * N is streamed in chunks; only M x M matrices and O(N) vectors persist on the device.          */
 typedef struct gpb200_fitc gpb200_fitc;
 int  gpb200_fitc_create(gpb200_fitc** out, int device);
@@ -183,6 +183,8 @@ int  gpb200_fitc_factorize(gpb200_fitc* f, const double* theta, double log_noise
 /* alpha = Sigma^-1 r, logdet(Sigma), mll = -(r'alpha + logdet + N log 2pi)/2 */
 int  gpb200_fitc_mll(gpb200_fitc* f, const double* y_minus_mean, double* alpha, double* mll, double* logdet);
 int  gpb200_fitc_grad_noise(gpb200_fitc* f, double* dmll_noise);
+/* dmll_kernel[n_theta], full parameter vector of the un-fixed kernel tree (as gpb200_grad_kernel) */
+int  gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel);
 /* mu_minus_mean[Ms], var[Ms] (may be NULL; not clamped) */
 int  gpb200_fitc_predict(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ldxs, double* mu_minus_mean, double* var);
 int64_t gpb200_fitc_launch_count(gpb200_fitc* f);

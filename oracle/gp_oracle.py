@@ -393,3 +393,40 @@ def fitc_predict(spec, X, Xu, f, Xs, mspec=("MeanZero",)):
     q = np.sum(sl.solve_triangular(f["Uuu"], Kux, trans="T", lower=False) ** 2, axis=0)
     s = np.sum(sl.solve_triangular(f["Us"], Kux, trans="T", lower=False) ** 2, axis=0)
     return mu, np.maximum(_kdiag(spec, Xs) - q + s, 0.0)
+
+
+def fitc_dmll_kern(spec, X, Xu, f):
+    """Kernel-parameter gradient of the FITC mll, restating the reference literally:
+    SoR part  dmll_kern!(..., ::SubsetOfRegsStrategy)   src/sparse/subsetofregressors.jl:219-253
+              with precompute! (Kuu⁻¹Kuf, Kuu⁻¹KufΣ⁻¹y, Σ⁻¹Kfu)  subsetofregressors.jl:140-151
+    FITC part dmll_kern!(..., ::FullyIndepStrat)         src/sparse/fully_indep_train_conditional.jl:200-234
+    `f` = result of fitc_fit (dense N x M matrices: small sizes only)."""
+    import scipy.linalg as sl
+    X = np.ascontiguousarray(X, dtype=np.float64); Xu = np.ascontiguousarray(Xu, dtype=np.float64)
+    n = X.shape[0]
+    alpha, Lam, Uuu, Us = f["alpha"], f["Lam"], f["Uuu"], f["Us"]
+    Kuf, gKuf = cov_and_grads(spec, Xu, X, True)
+    _, gKuu = cov_and_grads(spec, Xu, None, True)
+    gKdiag = [np.array([cov_and_grads(spec, X[i:i + 1], X[i:i + 1], True)[1][p][0, 0] for i in range(n)])
+              for p in range(len(gKuu))]
+    KuuinvKuf = _potrs_upper(Uuu, Kuf)                                   # Kuu \ Kuf            sor.jl:146
+    b = _potrs_upper(Uuu, Kuf @ alpha)                                   # Kuu⁻¹KufΣ⁻¹y         sor.jl:147
+
+    def solve_Sigma(B):                                                  # cK \ B  (fitc.jl:33-36)
+        Lk = sl.solve_triangular(Us, Kuf, trans="T", lower=False)
+        return (B - Lk.T @ (Lk @ (B / Lam[:, None]))) / Lam[:, None]
+
+    SinvKfu = solve_Sigma(Kuf.T)                                         # Σ⁻¹Kfu               sor.jl:148
+    out = []
+    for p in range(len(gKuu)):
+        dKuu, dKuf = gKuu[p], gKuf[p]
+        V = 2 * alpha @ (dKuf.T @ b) - b @ (dKuu @ b)                    # sor.jl:246-247
+        T = 2 * np.sum(solve_Sigma(dKuf.T) * KuuinvKuf.T)                # sor.jl:248
+        T -= np.sum(SinvKfu.T * (_potrs_upper(Uuu, dKuu) @ KuuinvKuf))   # sor.jl:249
+        g = (V - T) / 2.0
+        dLam = gKdiag[p] + np.sum(KuuinvKuf * (dKuu @ KuuinvKuf), axis=0) - 2 * np.sum(dKuf * KuuinvKuf, axis=0)   # fitc.jl:222-227
+        V2 = alpha @ (dLam * alpha)                                      # fitc.jl:228
+        Lsl = sl.solve_triangular(Us, Kuf / Lam, trans="T", lower=False)
+        T2 = np.sum(dLam / Lam) - np.sum(Lsl * (Lsl * dLam))             # trinvAB  fitc.jl:63-67
+        out.append(g + (V2 - T2) / 2.0)
+    return np.array(out)

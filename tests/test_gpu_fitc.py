@@ -36,6 +36,34 @@ def test_fitc_matches_oracle(N, M, d, kname):
     assert np.max(np.abs(s2 - vo)) <= 1e-7 * np.max(np.abs(vo)) + 1e-9
     my, sy = gp.predict_y(Xs.T)
     assert np.allclose(sy, s2 + np.exp(-2.0))
+    # kernel-parameter gradient (fitc.jl:200-234 + sor.jl:219-253); the literal oracle is O(N M P) dense: small N only
+    if N <= 3000:
+        gp.update_dmll()
+        gk = orc.fitc_dmll_kern(k.spec(), X, Xu, o)
+        assert np.allclose(gp.dmll[2:], gk, rtol=1e-6, atol=1e-7), (gp.dmll[2:], gk)
+        assert abs(gp.dmll[0] - o["dmll_noise"]) <= 1e-6 * abs(o["dmll_noise"]) + 1e-8
+
+
+def test_fitc_gradient_vs_finite_differences():
+    """test/test_sparse.jl:134-144: analytic gradient vs finite differences of the FITC mll (on the GPU path)."""
+    import gpb200 as g
+    rng = np.random.default_rng(11)
+    N, M, d = 6000, 150, 3
+    X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    k = g.SEArd([-0.4, -0.6, -0.5], 0.1)
+    gp = g.FITC(X.T, Xu.T, y, g.MeanZero(), k, -1.0)
+    gp.update_mll_and_dmll()
+    g0 = gp.dmll.copy()
+    p0 = [gp.logNoise] + k.get_params()
+    for i in range(len(p0)):
+        vals = []
+        for sgn in (+1, -1):
+            p = list(p0); p[i] += sgn * 1e-4
+            gp.logNoise = p[0]; k.set_params(p[1:]); gp.update_mll(); vals.append(gp.mll)
+        fd = (vals[0] - vals[1]) / 2e-4
+        assert abs(fd - g0[i]) <= 1e-5 * abs(fd) + 1e-4, (i, fd, g0[i])
+    gp.logNoise = p0[0]; k.set_params(p0[1:])
 
 
 def test_fitc_chunked_streaming_equals_single_chunk():
