@@ -63,6 +63,9 @@ struct gpb200_handle {
     double *noise_var = nullptr, *r0 = nullptr, *r1 = nullptr, *y1 = nullptr, *alpha = nullptr, *scal = nullptr;
     double *part = nullptr, *trace_out = nullptr;
     int* info_dev = nullptr;
+    int* flags = nullptr;                      // ready-flags of the single-launch triangular solves (2 x (Npad/128 + 1))
+    int trsv_fused = 1;
+    int max_resident_ctas = 0;
     int64_t n_noise = 1;
     double nugget = 0.0;
     CUtensorMap mapF{}, mapG{}, mapDinv{}, mapDinvT{};
@@ -191,6 +194,7 @@ void free_data(gpb200_handle* h) {
                        &h->pmu, &h->pvar, &h->pkdiag};
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
+    if (h->flags) { cudaFree(h->flags); h->flags = nullptr; }
     for (int i = 0; i < 2; ++i) { if (h->pack[i]) cudaFree(h->pack[i]); h->pack[i] = nullptr; }
     if (h->ag_send) cudaFree(h->ag_send);
     if (h->ag_recv) cudaFree(h->ag_recv);
@@ -610,9 +614,28 @@ int inverse_dist(gpb200_handle* h) {
 
 // alpha-type solve on device vectors: out = K_y^-1 rhs ; rhs (Npad, zero padded) is destroyed
 cudaError_t solve_device(gpb200_handle* h, double* rhs, double* tmp, double* out) {
+    const int nb = (int)(h->Npad / TILE);
+    // single-launch flag-synchronised solves need all Npad/128 CTAs co-resident (8 CTAs of 256 threads per SM)
+    if (h->trsv_fused && h->flags && nb <= h->max_resident_ctas) {
+        cudaError_t e = trsv_lower_fwd_fused(h->F, h->ld, h->Dinv, rhs, tmp, h->Npad, h->flags, h->st, &h->launches);
+        if (e != cudaSuccess) return e;
+        return trsv_lower_bwd_fused(h->F, h->ld, h->DinvT, tmp, out, h->Npad, h->flags + nb + 1, h->st, &h->launches);
+    }
     cudaError_t e = trsv_lower_fwd(h->F, h->ld, h->Dinv, rhs, tmp, h->Npad, h->st, &h->launches);
     if (e != cudaSuccess) return e;
     return trsv_lower_bwd(h->F, h->ld, h->DinvT, tmp, out, h->Npad, h->st, &h->launches);
+}
+
+// after a stream sync: did the watchdog of the single-launch solves fire?
+int check_trsv_watchdog(gpb200_handle* h) {
+    if (!h->trsv_fused || !h->flags) return GPB200_OK;
+    const int nb = (int)(h->Npad / TILE);
+    if (nb > h->max_resident_ctas) return GPB200_OK;
+    int e[2] = {0, 0};
+    CK(cudaMemcpy(&e[0], h->flags + nb, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&e[1], h->flags + 2 * nb + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e[0] || e[1]) return fail(h, GPB200_ECUDA, "triangular solve watchdog fired (a ready-flag never arrived)");
+    return GPB200_OK;
 }
 
 int upload_padded(gpb200_handle* h, double* dst, const double* src_host) {
@@ -793,6 +816,7 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
         h->dist_nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "trsv_fused")) { h->trsv_fused = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "profile")) {
         h->profile = value ? 1 : 0;
         h->ms[6] = h->ms[7] = h->ms[8] = 0.0;
@@ -846,6 +870,12 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
         CK(cudaMalloc(&h->r1, nv)); CK(cudaMalloc(&h->y1, nv)); CK(cudaMalloc(&h->alpha, nv));
         CK(cudaMalloc(&h->scal, sizeof(double) * 16));
         CK(cudaMalloc(&h->info_dev, sizeof(int)));
+        CK(cudaMalloc(&h->flags, sizeof(int) * 2 * (Npad / TILE + 1)));
+        {
+            int sms = 0;
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            h->max_resident_ctas = sms * 4;            // conservative: 4 CTAs of 256 threads per SM
+        }
         const int64_t T = Npad / TILE;
         CK(cudaMalloc(&h->part, sizeof(double) * (size_t)(T * (T + 1) / 2) * (GPB200_MAX_THETA + 1)));
         CK(cudaMalloc(&h->trace_out, sizeof(double) * (GPB200_MAX_THETA + 1)));
@@ -998,7 +1028,7 @@ int gpb200_solve(gpb200_handle* h, const double* rhs, double* out) {
     CK(solve_device(h, h->r1, h->y1, h->r0));
     CK(cudaMemcpyAsync(out, h->r0, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    return GPB200_OK;
+    return check_trsv_watchdog(h);
 }
 
 int gpb200_mll(gpb200_handle* h, const double* y_minus_mean, double* alpha, double* mll) {
@@ -1019,6 +1049,7 @@ int gpb200_mll(gpb200_handle* h, const double* y_minus_mean, double* alpha, doub
     CK(cudaEventRecord(h->ev1, h->st));
     CK(cudaStreamSynchronize(h->st));
     h->ms[2] = ev_ms(h->ev0, h->ev1);
+    { int rcw = check_trsv_watchdog(h); if (rcw) return rcw; }
     *mll = -(s[0] + s[1] + LOG2PI * (double)h->N) / 2.0;    // src/GPE.jl:210
     h->alpha_ready = true;
     return GPB200_OK;

@@ -53,6 +53,41 @@ __global__ void __launch_bounds__(NT) gram_lower_kernel(const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double mh = 0.0, s2 = 0.0;
     if (FAST) { mh = -0.5 / P.par[0]; s2 = P.par[1]; }
+    if (FAST && d <= 8) {
+        // register-cached variant: the lane's 4 column points live in registers, a row point is read
+        // once per row (8 broadcast LDS) -> 2 LDS per output instead of 16: FP64-ALU bound, not LSU bound
+        double xjr[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = (q >> 1) * 64 + lane * 2 + (q & 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xjr[q][k] = (k < d) ? sXj[c * ds + k] : 0.0;
+        }
+#pragma unroll 1
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = warp * 16 + rr;
+            const long long gi = (long long)bm * TB + r;
+            double xir[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xir[k] = (k < d) ? sXi[r * ds + k] : 0.0;
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long gj = (long long)bn * TB + (q >> 1) * 64 + lane * 2 + (q & 1);
+                double r2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const double df = xir[k] - xjr[q][k]; r2 += df * df; }
+                double kv = s2 * exp(mh * r2);
+                if (gi >= N || gj >= N) kv = (gi == gj) ? 1.0 : 0.0;
+                else if (gi == gj) kv += ((n_noise == 1) ? noise_var[0] : noise_var[gi]) + nugget;
+                v[q] = kv;
+            }
+            double* row = G + gi * ldg + (long long)bn * TB + lane * 2;
+            *reinterpret_cast<double2*>(row) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(row + 64) = make_double2(v[2], v[3]);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int rr = 0; rr < 16; ++rr) {
         const int r = warp * 16 + rr;

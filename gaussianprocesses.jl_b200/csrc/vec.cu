@@ -303,6 +303,119 @@ cudaError_t scale_launch(int mode, double* A, int64_t ld, int64_t nrows, int64_t
     return cudaGetLastError();
 }
 
+// ---- single-launch ("sync-free") triangular solves -------------------------------------------------
+// One CTA per 128-row block, all co-resident; CTA b consumes the solution blocks y_i (i < b) as their
+// ready-flags appear, then publishes y_b.  Dependencies always point to lower blockIdx, which the
+// hardware scheduler starts first, and 2*Npad/128 CTAs of 256 threads fit on the chip at once.  The two
+// tiles on the critical chain (L[b,b-1] and the inverted diagonal tile) are prefetched into L2 before
+// the CTA starts waiting.  A watchdog turns a missing flag into an error code instead of a hang.
+namespace {
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_tile_l2(const double* M, long long ld) {
+    // 128 rows x 1 KB: 8 lines of 128 B per row
+    for (int idx = threadIdx.x; idx < T * 8; idx += blockDim.x) {
+        const double* p = M + (long long)(idx >> 3) * ld + (idx & 7) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+}
+__device__ __forceinline__ bool wait_flag(const int* flag, int* err) {
+    long long spins = 0;
+    while (ld_acquire(flag) == 0) {
+        if (++spins > (1LL << 26)) { atomicExch(err, 1); return false; }
+        __nanosleep(20);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) trsv_fwd_persistent(const double* __restrict__ F, long long ldf, const double* __restrict__ Dinv,
+                                                           const double* __restrict__ r, double* __restrict__ y,
+                                                           int* __restrict__ flags, int* __restrict__ err) {
+    __shared__ double sAcc[T], sY[T], sO[T];
+    __shared__ int ok;
+    const int b = blockIdx.x;
+    const long long q = (long long)b * T;
+    if (threadIdx.x < T) sAcc[threadIdx.x] = r[q + threadIdx.x];
+    prefetch_tile_l2(Dinv + q * T, T);
+    if (b > 0) prefetch_tile_l2(F + q * ldf + (q - T), ldf);
+    __syncthreads();
+    for (int i = 0; i < b; ++i) {
+        if (threadIdx.x == 0) ok = wait_flag(flags + i, err) ? 1 : 0;
+        __syncthreads();
+        if (!ok) return;
+        if (threadIdx.x < T) sY[threadIdx.x] = __ldcg(y + (long long)i * T + threadIdx.x);
+        __syncthreads();
+        tile_matvec(F + q * ldf + (long long)i * T, ldf, sY, sO);
+        __syncthreads();
+        if (threadIdx.x < T) sAcc[threadIdx.x] -= sO[threadIdx.x];
+        __syncthreads();
+    }
+    tile_matvec(Dinv + q * T, T, sAcc, sO);               // y_b = W_bb (r_b - sum_i L_bi y_i)
+    __syncthreads();
+    if (threadIdx.x < T) y[q + threadIdx.x] = sO[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flags + b, 1);
+}
+
+__global__ void __launch_bounds__(256) trsv_bwd_persistent(const double* __restrict__ F, long long ldf, const double* __restrict__ DinvT,
+                                                           const double* __restrict__ z, double* __restrict__ a,
+                                                           int* __restrict__ flags, int* __restrict__ err, int nb) {
+    __shared__ double sAcc[T], sA[T], sO[T], sC[T];
+    __shared__ int ok;
+    const int b = nb - 1 - blockIdx.x;                     // dependencies (blocks > b) have lower blockIdx
+    const long long q = (long long)b * T;
+    if (threadIdx.x < T) sAcc[threadIdx.x] = z[q + threadIdx.x];
+    prefetch_tile_l2(DinvT + q * T, T);
+    if (b + 1 < nb) prefetch_tile_l2(F + (q + T) * ldf + q, ldf);
+    __syncthreads();
+    for (int i = nb - 1; i > b; --i) {
+        if (threadIdx.x == 0) ok = wait_flag(flags + i, err) ? 1 : 0;
+        __syncthreads();
+        if (!ok) return;
+        if (threadIdx.x < T) sA[threadIdx.x] = __ldcg(a + (long long)i * T + threadIdx.x);
+        __syncthreads();
+        tile_matvec_t(F + (long long)i * T * ldf + q, ldf, sA, sO, sC);     // L[i-block, b-block]' a_i
+        __syncthreads();
+        if (threadIdx.x < T) sAcc[threadIdx.x] -= sO[threadIdx.x];
+        __syncthreads();
+    }
+    tile_matvec(DinvT + q * T, T, sAcc, sO);              // a_b = W_bb' (z_b - sum_i L_ib' a_i)
+    __syncthreads();
+    if (threadIdx.x < T) a[q + threadIdx.x] = sO[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flags + b, 1);
+}
+}  // namespace
+
+// flags: int[Npad/128 + 1] scratch (last entry = watchdog error flag); returns cudaErrorLaunchFailure-free:
+// the caller reads flags[nb] after the stream sync.
+cudaError_t trsv_lower_fwd_fused(const double* F, int64_t ldf, const double* Dinv, const double* r, double* y, int64_t Npad,
+                                 int* flags, cudaStream_t st, int64_t* launches) {
+    const int nb = (int)(Npad / T);
+    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (nb + 1), st);
+    if (e != cudaSuccess) return e;
+    trsv_fwd_persistent<<<nb, 256, 0, st>>>(F, ldf, Dinv, r, y, flags, flags + nb);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+cudaError_t trsv_lower_bwd_fused(const double* F, int64_t ldf, const double* DinvT, const double* z, double* a, int64_t Npad,
+                                 int* flags, cudaStream_t st, int64_t* launches) {
+    const int nb = (int)(Npad / T);
+    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (nb + 1), st);
+    if (e != cudaSuccess) return e;
+    trsv_bwd_persistent<<<nb, 256, 0, st>>>(F, ldf, DinvT, z, a, flags, flags + nb, nb);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
 cudaError_t trsv_lower_fwd(const double* F, int64_t ldf, const double* Dinv, double* r, double* y, int64_t Npad,
                            cudaStream_t st, int64_t* launches) {
     const int nb = (int)(Npad / T);

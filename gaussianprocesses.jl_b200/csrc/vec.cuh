@@ -31,3 +31,8 @@ cudaError_t colscale_launch(double* A, int64_t ld, int64_t nrows, int64_t ncols,
 cudaError_t symmetrize_launch(double* A, int64_t ld, int64_t n, cudaStream_t st);
 cudaError_t fitc_wuu_launch(double* Wuu, const double* T, const double* Kinv, const double* Sinv, int64_t ld, int64_t n,
                             const double* beta, cudaStream_t st);
+// single-launch variants (flag-synchronised CTAs); flags: int[Npad/128 + 1], flags[Npad/128] != 0 after the run = watchdog fired
+cudaError_t trsv_lower_fwd_fused(const double* F, int64_t ldf, const double* Dinv, const double* r, double* y, int64_t Npad,
+                                 int* flags, cudaStream_t st, int64_t* launches);
+cudaError_t trsv_lower_bwd_fused(const double* F, int64_t ldf, const double* DinvT, const double* z, double* a, int64_t Npad,
+                                 int* flags, cudaStream_t st, int64_t* launches);
