@@ -65,6 +65,7 @@ struct gpb200_handle {
     int* info_dev = nullptr;
     int* flags = nullptr;                      // ready-flags of the single-launch triangular solves (2 x (Npad/128 + 1))
     int trsv_fused = 1;
+    int leaf_variant = 1;
     int max_resident_ctas = 0;
     int64_t n_noise = 1;
     double nugget = 0.0;
@@ -120,6 +121,7 @@ struct gpb200_fitc {
     double *gpart = nullptr, *gacc = nullptr, *gtmp = nullptr;
     CUtensorMap mapAt{}, mapC{}, mapCt{}, mapH{}, mapT{};
     bool grad_ws = false;
+    int mode = 0;                    // 0 FITC, 1 DTC, 2 SoR (Lambda = sigma^2 I; SoR also drops K_xx - Q_xx from the predictive variance)
     double noise_var = 0.0;
     bool has_data = false, has_kernel = false, factored = false, alpha_ready = false;
     std::string err;
@@ -329,7 +331,7 @@ cudaError_t chol_panel(gpb200_handle* h, int p, int n, int s) {
     cudaError_t e;
     if (s == TILE) {
         ++h->launches;
-        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st);
+        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st, h->leaf_variant);
         if (e != cudaSuccess) return e;
         const int below = Np - p - TILE;
         return below > 0 ? panel_trsm_leaf(h, p + TILE, below, p) : cudaSuccess;
@@ -817,6 +819,7 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "trsv_fused")) { h->trsv_fused = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "leaf")) { h->leaf_variant = value ? 1 : 0; h->factored = h->inv_ready = false; return GPB200_OK; }
     if (!strcmp(key, "profile")) {
         h->profile = value ? 1 : 0;
         h->ms[6] = h->ms[7] = h->ms[8] = 0.0;
@@ -1422,13 +1425,19 @@ int gpb200_fitc_factorize(gpb200_fitc* f, const double* theta, double log_noise)
     for (int64_t r0 = 0; r0 < f->N; r0 += f->Nc) {
         const int64_t nc = std::min(f->Nc, f->N - r0);
         const double* xr = f->x + r0 * f->d;
-        // Lambda_i = sigma^2 + K_ii - |L_uu^-1 K_ui|^2   (fitc.jl:146-148)
-        FCK(fitc_kfu(f, xr, nc));
-        FCK(trsm_rec_buf(eu, bA, (int)f->Nc, 0, (int)f->Mpad));
-        eu->launches += 3;
-        FCK(kdiag_launch(eu->prog, xr, f->d, nc, f->tmpc, st));
-        FCK(rowvar_launch(f->bufA, f->Mpad, f->tmpc, nc, f->Mpad, f->tmpc2, st));
-        FCK(ew_launch(0, nc, f->lam + r0, f->tmpc2, nullptr, nullptr, f->noise_var, st));
+        if (f->mode == 0) {
+            // Lambda_i = sigma^2 + K_ii - |L_uu^-1 K_ui|^2   (fitc.jl:146-148)
+            FCK(fitc_kfu(f, xr, nc));
+            FCK(trsm_rec_buf(eu, bA, (int)f->Nc, 0, (int)f->Mpad));
+            eu->launches += 3;
+            FCK(kdiag_launch(eu->prog, xr, f->d, nc, f->tmpc, st));
+            FCK(rowvar_launch(f->bufA, f->Mpad, f->tmpc, nc, f->Mpad, f->tmpc2, st));
+            FCK(ew_launch(0, nc, f->lam + r0, f->tmpc2, nullptr, nullptr, f->noise_var, st));
+        } else {
+            // SoR / DTC: Lambda = sigma^2 I   (subsetofregressors.jl:100: exp(-2 logNoise) * Kuf * Kfu + Kuu)
+            ++eu->launches;
+            FCK(ew_launch(0, nc, f->lam + r0, f->zeroc, nullptr, nullptr, f->noise_var, st));
+        }
         // Sigma_QR += K_uf Lambda^-1 K_fu   (fitc.jl:150), as (K_uf Lambda^-1/2)(K_uf Lambda^-1/2)'
         FCK(fitc_kuf(f, xr, nc));
         ++eu->launches;
@@ -1547,7 +1556,10 @@ int gpb200_fitc_predict(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ld
             FCK(kdiag_launch(eu->prog, f->xs, f->d, mc, f->tmpc, st));
             FCK(rowvar_launch(f->bufA, f->Mpad, f->tmpc, mc, f->Mpad, f->tmpc2, st));       // k_xx - q
             FCK(rowvar_launch(f->bufB, f->Mpad, f->zeroc, mc, f->Mpad, f->w, st));          // -s
-            FCK(ew_launch(6, mc, f->tmpc, f->tmpc2, f->w, nullptr, 0.0, st));               // k_xx - q + s
+            if (f->mode == 2) {                                                             // SoR: K_xu S^-1 K_ux only (sor.jl:302-321)
+                FCK(cudaMemsetAsync(f->tmpc2, 0, sizeof(double) * mc, st));
+            }
+            FCK(ew_launch(6, mc, f->tmpc, f->tmpc2, f->w, nullptr, 0.0, st));               // [k_xx - q] + s
             FCK(cudaMemcpyAsync(var + m0, f->tmpc, sizeof(double) * mc, cudaMemcpyDeviceToHost, st));
         }
         FCK(cudaStreamSynchronize(st));
@@ -1628,7 +1640,8 @@ int gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel) {
         }
         eu->launches += 2;
         FCK(rowdot2_launch(f->bufA, f->bufB, Mp, nc, Mp, f->tmpc, st));
-        FCK(fitc_g_launch(nc, f->alpha + r0, f->lam + r0, f->tmpc, f->gvec + r0, st));
+        if (f->mode == 0) FCK(fitc_g_launch(nc, f->alpha + r0, f->lam + r0, f->tmpc, f->gvec + r0, st));
+        else FCK(cudaMemsetAsync(f->gvec + r0, 0, sizeof(double) * nc, st));       // SoR part only (sor.jl:219-253)
         {   // P1 = K_fu K_uu^-1 -> bufC
             GemmDesc g = gemm_desc_default();
             g.A = GemmOperand{bA, bufNone(), 0, 0};
@@ -1640,6 +1653,7 @@ int gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel) {
         FCK(fitc_wfu_launch(f->bufB, f->bufC, Mp, nc, f->M, f->alpha + r0, f->lam + r0, f->gvec + r0, f->betav, st));
         FCK(trace_rect_launch(eu->prog, xr, f->d, nc, eu->x, f->d, f->M, f->d, f->bufB, Mp, f->gpart, f->gtmp, st));
         FCK(ew_launch(2, np, f->gacc, f->gtmp, nullptr, nullptr, 0.0, st));
+        if (f->mode != 0) continue;                                       // no Lambda-derivative terms for SoR / DTC
         // diagonal term sum_i g_i dK_ii/dθ_p (scratch: bufC as np x nc)
         FCK(kdiag_grad_launch(eu->prog, xr, f->d, nc, f->gvec + r0, f->bufC, st));
         for (int p = 0; p < np; ++p) { ++eu->launches; FCK(sum_launch(f->bufC + (size_t)p * nc, nc, f->gtmp + p, st)); }
@@ -1677,6 +1691,12 @@ int gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel) {
     FCK(cudaMemcpyAsync(out.data(), f->gacc, sizeof(double) * np, cudaMemcpyDeviceToHost, st));
     FCK(cudaStreamSynchronize(st));
     for (int p = 0; p < np; ++p) dmll_kernel[p] = 0.5 * out[p];
+    return GPB200_OK;
+}
+
+int gpb200_fitc_set_mode(gpb200_fitc* f, int mode) {
+    if (!f || mode < 0 || mode > 2) return GPB200_EINVAL;
+    f->mode = mode; f->factored = f->alpha_ready = false;
     return GPB200_OK;
 }
 

@@ -6,5 +6,5 @@ from .kernels import (Kernel, SEIso, SEArd, SE, Mat12Iso, Mat32Iso, Mat52Iso, Ma
                       FixedKernel, fix, flatten)
 from .means import Mean, MeanZero, MeanConst, MeanLin
 from .gpe import GPE, GP
-from .sparse import FITC
+from .sparse import FITC, DTC, SoR
 from . import dist

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "gpb200_fitc_grad_noise": (C.c_int, [_H, _dp]),
     "gpb200_fitc_grad_kernel": (C.c_int, [_H, _dp]),
     "gpb200_fitc_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp]),
+    "gpb200_fitc_set_mode": (C.c_int, [_H, C.c_int]),
     "gpb200_fitc_launch_count": (C.c_int64, [_H]),
     "gpb200_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
 }
@@ -349,6 +350,10 @@ class FitcEngine:
         self._check(self._lib.gpb200_fitc_predict(self._h, Ms, _as_dp(xs_pm), d, _as_dp(mu),
                                                   _as_dp(var) if want_var else None), "fitc_predict")
         return mu, var
+
+    def set_mode(self, mode):
+        """0 FITC, 1 DTC, 2 SoR."""
+        self._check(self._lib.gpb200_fitc_set_mode(self._h, int(mode)), "fitc_set_mode")
 
     def launch_count(self):
         return int(self._lib.gpb200_fitc_launch_count(self._h))

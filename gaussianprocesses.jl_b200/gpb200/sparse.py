@@ -13,6 +13,8 @@ from .means import MeanZero
 
 
 class FITC:
+    _mode = 0
+
     def __init__(self, x, Xu, y, mean=None, kernel=None, logNoise=-2.0, device=0):
         self.mean = mean if mean is not None else MeanZero()
         self.kernel = kernel
@@ -25,6 +27,7 @@ class FITC:
             raise ValueError("Input and output observations must have consistent dimensions.")
         self._xpm = np.ascontiguousarray(self.x.T)
         self._eng = capi.FitcEngine(device)
+        self._eng.set_mode(self._mode)
         self._eng.set_data(self._xpm, np.ascontiguousarray(self.Xu.T))
         ops, dims, theta, exposed = flatten(kernel, self.dim)
         self._exposed = exposed
@@ -80,3 +83,14 @@ class FITC:
     def predict_y(self, x):
         mu, s2 = self.predict_f(x)
         return mu, s2 + self.noise_variance()
+
+
+class DTC(FITC):
+    """Deterministic Training Conditional (src/sparse/determ_train_conditional.jl): SoR likelihood, FITC-style
+    predictive variance."""
+    _mode = 1
+
+
+class SoR(FITC):
+    """Subset of Regressors (src/sparse/subsetofregressors.jl)."""
+    _mode = 2

@@ -187,6 +187,11 @@ int  gpb200_fitc_grad_noise(gpb200_fitc* f, double* dmll_noise);
 int  gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel);
 /* mu_minus_mean[Ms], var[Ms] (may be NULL; not clamped) */
 int  gpb200_fitc_predict(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ldxs, double* mu_minus_mean, double* var);
+/* 0 = FITC (default), 1 = DTC (src/sparse/determ_train_conditional.jl), 2 = SoR
+ * (src/sparse/subsetofregressors.jl): the two share Lambda = sigma^2 I (sor.jl:96-106, `\` sor.jl:50,
+ * logdet sor.jl:53, dmll_noise sor.jl:159-166, dmll_kern! sor.jl:219-253); SoR's predictive covariance is
+ * K_xu S^-1 K_ux (sor.jl:302-321), DTC's adds K_xx - Q_xx (dtc.jl:41-59).                         */
+int  gpb200_fitc_set_mode(gpb200_fitc* f, int mode);
 int64_t gpb200_fitc_launch_count(gpb200_fitc* f);
 
 #ifdef __cplusplus

@@ -346,7 +346,7 @@ def predict_f(spec, X, f, Xs, mspec=("MeanZero",), full_cov=False):
 # ----------------------------------------------------------------------------------------------
 # FITC sparse strategy (src/sparse/fully_indep_train_conditional.jl), restated with dense numpy
 # ----------------------------------------------------------------------------------------------
-def fitc_fit(spec, X, Xu, y, log_noise, mspec=("MeanZero",)):
+def fitc_fit(spec, X, Xu, y, log_noise, mspec=("MeanZero",), mode="FITC"):
     """update_cK!(::FullyIndepPDMat) (fitc.jl:134-156) + `\\` (fitc.jl:33-36) + logdet (fitc.jl:77) + mll."""
     import scipy.linalg as sl
     X = np.ascontiguousarray(X, dtype=np.float64); Xu = np.ascontiguousarray(Xu, dtype=np.float64)
@@ -359,6 +359,8 @@ def fitc_fit(spec, X, Xu, y, log_noise, mspec=("MeanZero",)):
     W = sl.solve_triangular(Uuu, Kuf, trans="T", lower=False)   # U^-T Kuf ; invquad = column norms  fitc.jl:147
     Qdiag = np.sum(W * W, axis=0)
     Lam = math.exp(2 * log_noise) + Kdiag - Qdiag               # fitc.jl:148
+    if mode != "FITC":                                          # SoR / DTC: Σ ≈ Qff + σ²I  (sor.jl:96-106)
+        Lam = np.full(n, math.exp(2 * log_noise))
     SQR = Kuf @ (Kuf / Lam).T + Kuu + 1e-10 * np.eye(Xu.shape[0])     # fitc.jl:150-153
     Us = _potrf_upper(SQR)
     mu, MG = mean_and_grads(mspec, X)
@@ -371,7 +373,7 @@ def fitc_fit(spec, X, Xu, y, log_noise, mspec=("MeanZero",)):
     dnoise = math.exp(2 * log_noise) * (alpha @ alpha - np.sum(1.0 / Lam) + np.sum(LkL * LkL))   # fitc.jl:243-257
     alpha_u = _potrs_upper(Us, Kuf @ (r / Lam))                 # fitc.jl:279-286
     Sigma = (W.T @ W + np.diag(Lam)) if n <= 4096 else None      # Matrix(::FullyIndepPDMat)  fitc.jl:78-83
-    return dict(alpha=alpha, mll=mll, logdet=logdet, Lam=Lam, Uuu=Uuu, Us=Us, alpha_u=alpha_u, dmll_noise=dnoise,
+    return dict(mode=mode, alpha=alpha, mll=mll, logdet=logdet, Lam=Lam, Uuu=Uuu, Us=Us, alpha_u=alpha_u, dmll_noise=dnoise,
                 dmll_mean=MG.T @ alpha, Sigma=Sigma, resid=r)
 
 
@@ -392,6 +394,8 @@ def fitc_predict(spec, X, Xu, f, Xs, mspec=("MeanZero",)):
     mu = mx + Kux.T @ f["alpha_u"]
     q = np.sum(sl.solve_triangular(f["Uuu"], Kux, trans="T", lower=False) ** 2, axis=0)
     s = np.sum(sl.solve_triangular(f["Us"], Kux, trans="T", lower=False) ** 2, axis=0)
+    if f.get("mode", "FITC") == "SoR":                            # sor.jl:302-321: Σ = Kxu ΣQR⁻¹ Kux
+        return mu, np.maximum(s, 0.0)
     return mu, np.maximum(_kdiag(spec, Xs) - q + s, 0.0)
 
 
@@ -424,6 +428,9 @@ def fitc_dmll_kern(spec, X, Xu, f):
         T = 2 * np.sum(solve_Sigma(dKuf.T) * KuuinvKuf.T)                # sor.jl:248
         T -= np.sum(SinvKfu.T * (_potrs_upper(Uuu, dKuu) @ KuuinvKuf))   # sor.jl:249
         g = (V - T) / 2.0
+        if f.get("mode", "FITC") != "FITC":                              # SoR / DTC: no Λ-derivative part
+            out.append(g)
+            continue
         dLam = gKdiag[p] + np.sum(KuuinvKuf * (dKuu @ KuuinvKuf), axis=0) - 2 * np.sum(dKuf * KuuinvKuf, axis=0)   # fitc.jl:222-227
         V2 = alpha @ (dLam * alpha)                                      # fitc.jl:228
         Lsl = sl.solve_triangular(Us, Kuf / Lam, trans="T", lower=False)

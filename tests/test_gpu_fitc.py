@@ -78,3 +78,28 @@ def test_fitc_chunked_streaming_equals_single_chunk():
     o = orc.fitc_fit(k.spec(), X, Xu, y, -1.0)          # O(N M) on the CPU: fine at this size
     assert abs(gp.mll - o["mll"]) <= 1e-9 * abs(o["mll"])
     assert _rel(gp.alpha, o["alpha"]) < 1e-7
+
+
+@pytest.mark.parametrize("mode", ["SoR", "DTC"])
+def test_sor_dtc_match_oracle(mode):
+    """SoR / DTC (subsetofregressors.jl, determ_train_conditional.jl): same engine with Lambda = sigma^2 I."""
+    import gpb200 as g
+    rng = np.random.default_rng(3)
+    N, M, d = 2500, 120, 3
+    X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    Xs = rng.standard_normal((40, d))
+    k = g.SEIso(-0.6, 0.2) * g.Const(0.1)
+    cls = g.SoR if mode == "SoR" else g.DTC
+    gp = cls(X.T, Xu.T, y, g.MeanZero(), k, -0.8)
+    gp.update_dmll()
+    o = orc.fitc_fit(k.spec(), X, Xu, y, -0.8, mode=mode)
+    assert abs(gp.mll - o["mll"]) <= 1e-9 * abs(o["mll"])
+    assert _rel(gp.alpha, o["alpha"]) < 1e-7
+    assert abs(gp.dmll[0] - o["dmll_noise"]) <= 1e-6 * abs(o["dmll_noise"]) + 1e-8
+    gk = orc.fitc_dmll_kern(k.spec(), X, Xu, o)
+    assert np.allclose(gp.dmll[1:], gk, rtol=1e-6, atol=1e-7), (gp.dmll[1:], gk)
+    mu, s2 = gp.predict_f(Xs.T)
+    mo, vo = orc.fitc_predict(k.spec(), X, Xu, o, Xs)
+    assert _rel(mu, mo) < 1e-7
+    assert np.max(np.abs(s2 - vo)) <= 1e-7 * np.max(np.abs(vo)) + 1e-9
