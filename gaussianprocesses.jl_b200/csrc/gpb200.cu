@@ -65,7 +65,6 @@ struct gpb200_handle {
     int* info_dev = nullptr;
     int* flags = nullptr;                      // ready-flags of the single-launch triangular solves (2 x (Npad/128 + 1))
     int trsv_fused = 1;
-    int leaf_variant = 1;
     int max_resident_ctas = 0;
     int64_t n_noise = 1;
     double nugget = 0.0;
@@ -331,7 +330,7 @@ cudaError_t chol_panel(gpb200_handle* h, int p, int n, int s) {
     cudaError_t e;
     if (s == TILE) {
         ++h->launches;
-        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st, h->leaf_variant);
+        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st);
         if (e != cudaSuccess) return e;
         const int below = Np - p - TILE;
         return below > 0 ? panel_trsm_leaf(h, p + TILE, below, p) : cudaSuccess;
@@ -819,7 +818,6 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "trsv_fused")) { h->trsv_fused = value ? 1 : 0; return GPB200_OK; }
-    if (!strcmp(key, "leaf")) { h->leaf_variant = value ? 1 : 0; h->factored = h->inv_ready = false; return GPB200_OK; }
     if (!strcmp(key, "profile")) {
         h->profile = value ? 1 : 0;
         h->ms[6] = h->ms[7] = h->ms[8] = 0.0;

@@ -4,5 +4,4 @@
 #include <stdint.h>
 // tiles at diagonal offsets p0 + b*tile_stride, b < ntiles.  *info must be initialised to INT_MAX.
 cudaError_t potrf128_launch(const double* G, int64_t ldg, double* F, int64_t ldf, double* Dinv, double* DinvT,
-                            double* logd, int* info, int p0, int ntiles, int tile_stride, cudaStream_t st, int variant = 1);
-// variant 0: one column per barrier step; 1 (default): 8-column panels factored warp-synchronously
+                            double* logd, int* info, int p0, int ntiles, int tile_stride, cudaStream_t st);
