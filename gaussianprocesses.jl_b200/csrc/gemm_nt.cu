@@ -41,6 +41,8 @@ struct GemmKP {
     int flags, zstep, m_lim, n_lim, k_lim;
     int a_has_sub, b_has_sub;
     int klo_off, bm_mod, bm_rem, bn_mod, bn_rem;
+    int n_peer;                  // extra copies of C stored into peer GPUs' buffers (NVLink P2P), same ldc/offsets
+    double* Cpeer[7];
     double alpha, beta;
 };
 
@@ -137,6 +139,9 @@ __device__ __forceinline__ void epilogue(const GemmKP& p, const TileCtx& t, doub
             }
             if (!diag_mask) {
                 *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+                // fused panel broadcast: the same tile goes straight into every peer's copy of the factor
+                for (int q = 0; q < p.n_peer; ++q)
+                    *reinterpret_cast<double2*>(p.Cpeer[q] + row * p.ldc + col) = make_double2(v0, v1);
             } else {
                 const int lr = lrow0 + i * 8, lc = lcol0 + j * 8;
                 if (lc + 1 <= lr) *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
@@ -374,6 +379,8 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     p.flags = d.flags; p.zstep = d.zstep; p.m_lim = d.m_lim; p.n_lim = d.n_lim; p.k_lim = d.k_lim;
     p.a_has_sub = d.A.sub.base != nullptr; p.b_has_sub = d.B.sub.base != nullptr;
     p.klo_off = d.klo_off; p.bm_mod = d.bm_mod; p.bm_rem = d.bm_rem; p.bn_mod = d.bn_mod; p.bn_rem = d.bn_rem;
+    p.n_peer = d.n_peer;
+    for (int q = 0; q < 7; ++q) p.Cpeer[q] = q < d.n_peer ? d.Cpeer[q] : nullptr;
     p.alpha = d.alpha; p.beta = d.beta;
     if (d.M <= 0 || d.N <= 0) return cudaSuccess;
     if ((d.M % BM) || (d.N % BN) || (d.K % BK)) return cudaErrorInvalidValue;

@@ -41,6 +41,8 @@ struct GemmDesc {
     int klo_off;        // GEMM_KLO_M: k starts at klo_off + bm*128 (row slice of a triangular operand)
     int bm_mod, bm_rem; // multi-GPU work split: only tile rows with bm % bm_mod == bm_rem (bm_mod <= 1: all)
     int bn_mod, bn_rem; // same for tile columns
+    int n_peer;         // fused broadcast: C is additionally stored to these peer-mapped buffers (not with LOWER_ONLY)
+    double* Cpeer[7];
 };
 
 static inline GemmDesc gemm_desc_default() {

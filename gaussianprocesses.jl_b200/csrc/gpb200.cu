@@ -99,6 +99,16 @@ struct gpb200_handle {
     cudaEvent_t ev_x = nullptr, ev_y = nullptr;
     double *ag_send = nullptr, *ag_recv = nullptr;
     size_t ag_send_elems = 0, ag_recv_elems = 0;
+    // fused panel broadcast over NVLink peer memory (CUDA IPC): peers' F / Dinv / DinvT / logd / signal words
+    bool p2p = false;
+    int n_peer = 0;
+    int peer_rank[7] = {0, 0, 0, 0, 0, 0, 0};
+    double *peer_F[7] = {}, *peer_Dinv[7] = {}, *peer_DinvT[7] = {}, *peer_logd[7] = {};
+    int* peer_sig[7] = {};
+    int* sig = nullptr;                        // sig[q] = last panel published by rank q (epoch * 65536 + b + 1); sig[8] = watchdog
+    int epoch = 0;
+    int** peer_sig_dev = nullptr;              // device array: &peer_sig[q][rank]
+    bool push_panel = false;                   // set while the owner factors a panel: leaf + leaf TRSM also store to the peers
     std::string err;
 };
 
@@ -196,6 +206,16 @@ void free_data(gpb200_handle* h) {
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
     if (h->flags) { cudaFree(h->flags); h->flags = nullptr; }
+    if (h->p2p) {
+        for (int q = 0; q < h->n_peer; ++q) {
+            cudaIpcCloseMemHandle(h->peer_F[q]); cudaIpcCloseMemHandle(h->peer_Dinv[q]);
+            cudaIpcCloseMemHandle(h->peer_DinvT[q]); cudaIpcCloseMemHandle(h->peer_logd[q]);
+            cudaIpcCloseMemHandle(h->peer_sig[q]);
+        }
+        h->p2p = false; h->n_peer = 0;
+    }
+    if (h->sig) { cudaFree(h->sig); h->sig = nullptr; }
+    if (h->peer_sig_dev) { cudaFree(h->peer_sig_dev); h->peer_sig_dev = nullptr; }
     for (int i = 0; i < 2; ++i) { if (h->pack[i]) cudaFree(h->pack[i]); h->pack[i] = nullptr; }
     if (h->ag_send) cudaFree(h->ag_send);
     if (h->ag_recv) cudaFree(h->ag_recv);
@@ -274,6 +294,10 @@ cudaError_t panel_trsm_leaf(gpb200_handle* h, int r0, int rows, int p) {
     g.B = GemmOperand{bufDinv(h), bufNone(), p, 0};
     g.C = h->F; g.ldc = h->ld; g.c_row0 = r0; g.c_col0 = p;
     g.M = rows; g.N = TILE; g.K = TILE;
+    if (h->push_panel) {                       // fused broadcast: the epilogue also writes the peers' factor
+        g.n_peer = h->n_peer;
+        for (int q = 0; q < h->n_peer; ++q) g.Cpeer[q] = h->peer_F[q];
+    }
     return launch_gemm(h, g);
 }
 // Schur update of the lower trapezoid G[r0.., r0..r0+cols) -= F[r0.., p..p+k) F[r0..r0+cols, p..p+k)'
@@ -330,7 +354,12 @@ cudaError_t chol_panel(gpb200_handle* h, int p, int n, int s) {
     cudaError_t e;
     if (s == TILE) {
         ++h->launches;
-        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st);
+        PotrfPeers pp{};
+        if (h->push_panel) {
+            pp.n = h->n_peer;
+            for (int q = 0; q < h->n_peer; ++q) { pp.F[q] = h->peer_F[q]; pp.Dinv[q] = h->peer_Dinv[q]; pp.DinvT[q] = h->peer_DinvT[q]; pp.logd[q] = h->peer_logd[q]; }
+        }
+        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st, &pp);
         if (e != cudaSuccess) return e;
         const int below = Np - p - TILE;
         return below > 0 ? panel_trsm_leaf(h, p + TILE, below, p) : cudaSuccess;
@@ -539,6 +568,87 @@ int cholesky_dist(gpb200_handle* h) {
             if (owner(jb) == me) CK(update(jb, b));
     }
     // first failing pivot over all ranks
+    CK(cudaEventRecord(h->ev_x, h->st));
+    CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
+    CKN(g_nccl.AllReduce(h->info_dev, h->info_dev, 1, ncclInt32, ncclMin, h->comm, h->st_comm));
+    CK(cudaEventRecord(h->ev_y, h->st_comm));
+    CK(cudaStreamWaitEvent(h->st, h->ev_y, 0));
+    return GPB200_OK;
+}
+
+
+// ---- device-side signalling for the fused (peer-memory) panel broadcast --------------------------
+__global__ void signal_peers_kernel(int* const* peer_sig_words, int n_peer, int value) {
+    // all panel stores of the preceding kernels are complete (stream order); make them visible
+    // system-wide before the flag
+    __threadfence_system();
+    if ((int)threadIdx.x < n_peer)
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_sig_words[threadIdx.x]), "r"(value) : "memory");
+}
+__global__ void wait_signal_kernel(const int* word, int target, int* err) {
+    long long spins = 0;
+    int v;
+    do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+        if (v >= target) break;
+        if (++spins > (1LL << 27)) { atomicExch(err, 1); break; }
+        __nanosleep(100);
+    } while (true);
+}
+
+// Cholesky over block columns with the panel broadcast FUSED into the kernels that produce the panel:
+// the tile leaf and the 128-wide TRSM GEMM store their outputs into every peer's F / Dinv / DinvT / logd
+// through NVLink-mapped pointers (CUDA IPC), then one tiny kernel raises a flag word in each peer; the
+// peers' streams wait on that word with a one-thread kernel.  No staging copy, no NCCL on the panel path.
+int cholesky_dist_p2p(gpb200_handle* h) {
+    const int Np = (int)h->Npad, R = h->nranks, me = h->rank;
+    const int NB = dist_block(h);
+    const int nblk = (Np + NB - 1) / NB;
+    auto bp = [&](int b) { return b * NB; };
+    auto bn = [&](int b) { return std::min(NB, Np - b * NB); };
+    auto owner = [&](int b) { return b % R; };
+    auto update = [&](int jb, int b) {
+        const int r0 = bp(jb);
+        return schur_update(h, r0, Np - r0, bn(jb), bp(b), bn(b));
+    };
+    // start barrier: no rank may push a new panel into a peer's factor while that peer still reads the
+    // previous evaluation's factor (inverse / predict); also makes the rare epoch wrap safe
+    if (++h->epoch >= 32000) { h->epoch = 1; CK(cudaMemsetAsync(h->sig, 0, sizeof(int) * 8, h->st)); }
+    const int base = h->epoch * 65536;
+    CK(cudaEventRecord(h->ev_x, h->st));
+    CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
+    CKN(g_nccl.AllReduce(h->sig + 12, h->sig + 12, 1, ncclInt32, ncclSum, h->comm, h->st_comm));
+    CK(cudaEventRecord(h->ev_y, h->st_comm));
+    CK(cudaStreamWaitEvent(h->st, h->ev_y, 0));
+    auto factor_and_publish = [&](int b) -> int {
+        h->push_panel = true;
+        cudaError_t e = chol_panel(h, bp(b), bn(b), NB);
+        h->push_panel = false;
+        CK(e);
+        ++h->launches;
+        signal_peers_kernel<<<1, 32, 0, h->st>>>(h->peer_sig_dev, h->n_peer, base + b + 1);
+        CK(cudaGetLastError());
+        return GPB200_OK;
+    };
+    if (owner(0) == me) { int rc = factor_and_publish(0); if (rc) return rc; }
+    for (int b = 0; b < nblk; ++b) {
+        if (owner(b) != me) {
+            ++h->launches;
+            wait_signal_kernel<<<1, 1, 0, h->st>>>(h->sig + owner(b), base + b + 1, h->sig + 8);
+            CK(cudaGetLastError());
+        }
+        bool did_next = false;
+        if (b + 1 < nblk && owner(b + 1) == me) {
+            CK(update(b + 1, b));
+            int rc = factor_and_publish(b + 1);
+            if (rc) return rc;
+            did_next = true;
+        }
+        for (int jb = b + 1 + (did_next ? 1 : 0); jb < nblk; ++jb)
+            if (owner(jb) == me) CK(update(jb, b));
+    }
+    // first failing pivot over all ranks; also the barrier that keeps the next evaluation from overwriting
+    // a panel a slower peer is still reading
     CK(cudaEventRecord(h->ev_x, h->st));
     CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
     CKN(g_nccl.AllReduce(h->info_dev, h->info_dev, 1, ncclInt32, ncclMin, h->comm, h->st_comm));
@@ -818,6 +928,10 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "trsv_fused")) { h->trsv_fused = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "p2p")) {                 // 0: NCCL panel broadcast even if peer memory is mapped
+        if (value && h->n_peer == 0) return fail(h, GPB200_ESTATE, "p2p: ipc_import first");
+        h->p2p = value != 0; return GPB200_OK;
+    }
     if (!strcmp(key, "profile")) {
         h->profile = value ? 1 : 0;
         h->ms[6] = h->ms[7] = h->ms[8] = 0.0;
@@ -872,6 +986,8 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
         CK(cudaMalloc(&h->scal, sizeof(double) * 16));
         CK(cudaMalloc(&h->info_dev, sizeof(int)));
         CK(cudaMalloc(&h->flags, sizeof(int) * 2 * (Npad / TILE + 1)));
+        CK(cudaMalloc(&h->sig, sizeof(int) * 16));
+        CK(cudaMemsetAsync(h->sig, 0, sizeof(int) * 16, h->st));
         {
             int sms = 0;
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -985,7 +1101,7 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
         CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld,
                              h->st, NBd / TILE, h->nranks, h->rank));
         CK(cudaEventRecord(h->ev1, h->st));
-        rc = cholesky_dist(h);
+        rc = h->p2p ? cholesky_dist_p2p(h) : cholesky_dist(h);
         if (rc) return rc;
     } else {
         CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld, h->st));
@@ -999,6 +1115,11 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
     profile_collect(h);
     h->ms[0] = ev_ms(h->ev0, h->ev1);
     h->ms[1] = ev_ms(h->ev1, h->ev2);
+    if (h->p2p) {
+        int wd = 0;
+        CK(cudaMemcpy(&wd, h->sig + 8, sizeof(int), cudaMemcpyDeviceToHost));
+        if (wd) return fail(h, GPB200_ECUDA, "panel signal watchdog fired (a peer never published its panel)");
+    }
     if (info != INT_MAX) {
         char buf[128];
         snprintf(buf, sizeof buf, "matrix is not positive definite; leading minor %d", info);
@@ -1244,6 +1365,55 @@ int gpb200_fp64_peak(gpb200_handle* h, double* tflops_dmma, double* tflops_dfma)
     CK(fp64_peak_measure(h->st, t));
     if (tflops_dmma) *tflops_dmma = t[0];
     if (tflops_dfma) *tflops_dfma = t[1];
+    return GPB200_OK;
+}
+
+
+#define GPB200_IPC_BYTES 512
+int gpb200_ipc_export(gpb200_handle* h, char* out) {
+    if (!h || !out) return GPB200_EINVAL;
+    if (!h->has_data) return fail(h, GPB200_ESTATE, "ipc_export: set_data first (buffers must exist)");
+    CK(cudaSetDevice(h->device));
+    memset(out, 0, GPB200_IPC_BYTES);
+    cudaIpcMemHandle_t hd[5];
+    CK(cudaIpcGetMemHandle(&hd[0], h->F));
+    CK(cudaIpcGetMemHandle(&hd[1], h->Dinv));
+    CK(cudaIpcGetMemHandle(&hd[2], h->DinvT));
+    CK(cudaIpcGetMemHandle(&hd[3], h->logd));
+    CK(cudaIpcGetMemHandle(&hd[4], h->sig));
+    static_assert(5 * sizeof(cudaIpcMemHandle_t) + 16 <= GPB200_IPC_BYTES, "ipc blob too small");
+    memcpy(out, hd, sizeof hd);
+    const int64_t np = h->Npad;
+    memcpy(out + sizeof hd, &np, sizeof np);
+    return GPB200_OK;
+}
+
+int gpb200_ipc_import(gpb200_handle* h, int nranks, const char* all) {
+    if (!h || !all) return GPB200_EINVAL;
+    if (nranks != h->nranks || nranks < 2 || nranks > 8) return fail(h, GPB200_EINVAL, "ipc_import: call comm_init first; 2..8 ranks");
+    CK(cudaSetDevice(h->device));
+    int n = 0;
+    for (int q = 0; q < nranks; ++q) {
+        if (q == h->rank) continue;
+        const char* blob = all + (size_t)q * GPB200_IPC_BYTES;
+        cudaIpcMemHandle_t hd[5];
+        memcpy(hd, blob, sizeof hd);
+        int64_t np = 0;
+        memcpy(&np, blob + sizeof hd, sizeof np);
+        if (np != h->Npad) return fail(h, GPB200_EINVAL, "ipc_import: peers hold a different problem size");
+        void* ptr[5];
+        for (int k = 0; k < 5; ++k) CK(cudaIpcOpenMemHandle(&ptr[k], hd[k], cudaIpcMemLazyEnablePeerAccess));
+        h->peer_rank[n] = q;
+        h->peer_F[n] = (double*)ptr[0]; h->peer_Dinv[n] = (double*)ptr[1]; h->peer_DinvT[n] = (double*)ptr[2];
+        h->peer_logd[n] = (double*)ptr[3]; h->peer_sig[n] = (int*)ptr[4];
+        ++n;
+    }
+    h->n_peer = n;
+    int* words[7];
+    for (int q = 0; q < n; ++q) words[q] = h->peer_sig[q] + h->rank;
+    if (!h->peer_sig_dev) CK(cudaMalloc(&h->peer_sig_dev, sizeof(int*) * 8));
+    CK(cudaMemcpy(h->peer_sig_dev, words, sizeof(int*) * n, cudaMemcpyHostToDevice));
+    h->p2p = true;
     return GPB200_OK;
 }
 

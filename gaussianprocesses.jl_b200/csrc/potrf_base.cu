@@ -29,7 +29,7 @@ constexpr int NTH = 512;
 __global__ void __launch_bounds__(NTH, 1)
 potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restrict__ F, long long ldf,
                     double* __restrict__ Dinv, double* __restrict__ DinvT, double* __restrict__ logd,
-                    int* __restrict__ info, int p0, int tile_stride) {
+                    int* __restrict__ info, int p0, int tile_stride, const PotrfPeers peers) {
     extern __shared__ double S[];                 // [128][129] + rs[128]
     double* rs = S + T * LDS;
     const int p = p0 + blockIdx.x * tile_stride;
@@ -89,7 +89,9 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
     __syncthreads();   // pivots + all columns published
     if (threadIdx.x < T) {
         const double d = rs[threadIdx.x];
-        logd[p + threadIdx.x] = log(d);
+        const double lg = log(d);
+        logd[p + threadIdx.x] = lg;
+        for (int q = 0; q < peers.n; ++q) peers.logd[q][p + threadIdx.x] = lg;
         rs[threadIdx.x] = 1.0 / sqrt(d);
     }
     __syncthreads();
@@ -100,6 +102,7 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
             const double v = S[m * LDS + j] * rs[j];
             S[m * LDS + j] = v;
             F[(long long)(p + m) * ldf + p + j] = v;
+            for (int q = 0; q < peers.n; ++q) peers.F[q][(long long)(p + m) * ldf + p + j] = v;
         }
     }
     __syncthreads();
@@ -146,9 +149,15 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
     for (int idx = threadIdx.x; idx < T * T; idx += NTH) {
         const int r = idx >> 7, c = idx & 127;
         // Dinv[r][c] = W[r][c] = S[c][r+1] for c <= r
-        Dinv[(long long)(p + r) * T + c] = (c <= r) ? S[c * LDS + r + 1] : 0.0;
+        const double wl = (c <= r) ? S[c * LDS + r + 1] : 0.0;
         // DinvT[r][c] = W[c][r] = S[r][c+1] for c >= r
-        DinvT[(long long)(p + r) * T + c] = (c >= r) ? S[r * LDS + c + 1] : 0.0;
+        const double wu = (c >= r) ? S[r * LDS + c + 1] : 0.0;
+        Dinv[(long long)(p + r) * T + c] = wl;
+        DinvT[(long long)(p + r) * T + c] = wu;
+        for (int q = 0; q < peers.n; ++q) {
+            peers.Dinv[q][(long long)(p + r) * T + c] = wl;
+            peers.DinvT[q][(long long)(p + r) * T + c] = wu;
+        }
     }
 }
 
@@ -157,13 +166,16 @@ bool g_attr_set = false;
 }  // namespace
 
 cudaError_t potrf128_launch(const double* G, int64_t ldg, double* F, int64_t ldf, double* Dinv, double* DinvT,
-                            double* logd, int* info, int p0, int ntiles, int tile_stride, cudaStream_t st) {
+                            double* logd, int* info, int p0, int ntiles, int tile_stride, cudaStream_t st,
+                            const PotrfPeers* peers) {
+    PotrfPeers pp{};
+    if (peers) pp = *peers;
     const size_t sm = (size_t)(T * LDS + T) * sizeof(double);
     if (!g_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(potrf128_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         g_attr_set = true;
     }
-    potrf128_inv_kernel<<<ntiles, NTH, sm, st>>>(G, ldg, F, ldf, Dinv, DinvT, logd, info, p0, tile_stride);
+    potrf128_inv_kernel<<<ntiles, NTH, sm, st>>>(G, ldg, F, ldf, Dinv, DinvT, logd, info, p0, tile_stride, pp);
     return cudaGetLastError();
 }

@@ -2,6 +2,15 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+// fused panel broadcast (multi-GPU): every output of the leaf is also stored into the peers' buffers (NVLink P2P)
+struct PotrfPeers {
+    int n;
+    double* F[7];
+    double* Dinv[7];
+    double* DinvT[7];
+    double* logd[7];
+};
 // tiles at diagonal offsets p0 + b*tile_stride, b < ntiles.  *info must be initialised to INT_MAX.
 cudaError_t potrf128_launch(const double* G, int64_t ldg, double* F, int64_t ldf, double* Dinv, double* DinvT,
-                            double* logd, int* info, int p0, int ntiles, int tile_stride, cudaStream_t st);
+                            double* logd, int* info, int p0, int ntiles, int tile_stride, cudaStream_t st,
+                            const PotrfPeers* peers = nullptr);

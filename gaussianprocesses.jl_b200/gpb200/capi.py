@@ -49,6 +49,8 @@ _SIGNATURES = {
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int64,
                                          C.c_int, C.c_int, _dp]),
     "gpb200_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "gpb200_ipc_export": (C.c_int, [_H, C.c_void_p]),
+    "gpb200_ipc_import": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "gpb200_fitc_create": (C.c_int, [C.POINTER(_H), C.c_int]),
     "gpb200_fitc_destroy": (None, [_H]),
     "gpb200_fitc_last_error": (C.c_char_p, [_H]),
@@ -250,6 +252,21 @@ class Engine:
         ib = C.create_string_buffer(bytes(id128), 128)
         self._check(self._lib.gpb200_comm_init(self._h, int(nranks), int(rank), C.cast(ib, C.c_char_p)), "comm_init")
         self.nranks, self.rank = int(nranks), int(rank)
+
+    IPC_BYTES = 512
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(self.IPC_BYTES)
+        self._check(self._lib.gpb200_ipc_export(self._h, C.cast(buf, C.c_void_p)), "ipc_export")
+        return buf.raw
+
+    def ipc_import(self, blobs):
+        """blobs: list of nranks byte strings in rank order (own entry ignored)."""
+        joined = b"".join(bytes(b) for b in blobs)
+        if len(joined) != self.IPC_BYTES * len(blobs):
+            raise ValueError("ipc_import: every blob must be %d bytes" % self.IPC_BYTES)
+        buf = C.create_string_buffer(joined, len(joined))
+        self._check(self._lib.gpb200_ipc_import(self._h, len(blobs), C.cast(buf, C.c_void_p)), "ipc_import")
 
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()

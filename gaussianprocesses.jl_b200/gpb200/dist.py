@@ -11,7 +11,7 @@ def broadcast_bytes(payload_or_none, src=0):
     return obj[0]
 
 
-def init_engine_comm(engine):
+def init_engine_comm(engine, p2p=True):
     """Join `engine` (one per rank) into one NCCL communicator spanning the default process group."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
@@ -19,6 +19,11 @@ def init_engine_comm(engine):
     rank, world = dist.get_rank(), dist.get_world_size()
     uid = broadcast_bytes(engine.nccl_unique_id() if rank == 0 else None, src=0)
     engine.comm_init(world, rank, uid)
+    if p2p and hasattr(engine, "ipc_export"):
+        # fused panel broadcast: map every peer's factor buffers over NVLink (CUDA IPC)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, engine.ipc_export())
+        engine.ipc_import(blobs)
     return world, rank
 
 

@@ -71,11 +71,14 @@ class GPE:
         self._eng.set_data(self._xpm)
         return self
 
-    def init_distributed(self):
+    def init_distributed(self, p2p=None):
         """Multi-GPU: join this rank's engine into the NCCL communicator of the torch.distributed
         default group (one process per GPU).  Every later update_*/predict call is collective."""
+        import os
         from .dist import init_engine_comm
-        world, rank = init_engine_comm(self._eng)
+        if p2p is None:
+            p2p = os.environ.get("GPB200_P2P", "1") != "0"
+        world, rank = init_engine_comm(self._eng, p2p=p2p)
         if world > 1:
             self.update_target()
         return world, rank

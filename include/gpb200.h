@@ -161,6 +161,14 @@ int  gpb200_dgemm_nt_device(gpb200_handle* h, int impl, int64_t M, int64_t N, in
  * Julia Distributed), every rank then joins.                                                */
 int  gpb200_nccl_unique_id(char* id128);
 int  gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128);
+/* Fused panel broadcast over NVLink peer memory (optional, after comm_init and set_data): every rank
+ * exports CUDA-IPC handles of its factor buffers (GPB200_IPC_BYTES bytes), the host layer all-gathers
+ * the blobs (rank order) and every rank imports them.  From then on the kernels that PRODUCE a panel
+ * (tile leaf, 128-wide TRSM GEMM) store it straight into all peers' buffers and raise a device-side
+ * flag; NCCL stays on the small collectives only.  Re-export after a gpb200_set_data that changes N. */
+#define GPB200_IPC_BYTES 512
+int  gpb200_ipc_export(gpb200_handle* h, char* out);
+int  gpb200_ipc_import(gpb200_handle* h, int nranks, const char* all_blobs);
 
 /* ---- sparse FITC strategy (src/sparse/fully_indep_train_conditional.jl) ------------------------
  * FITC(x, Xu, y, mean, kern, logNoise) (fitc.jl:335-338) == GPE(..., FullyIndepStrat(Xu)).

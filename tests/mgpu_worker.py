@@ -31,8 +31,17 @@ def main():
         Xs = rng.standard_normal((50, d))
         gp = gpb200.GPE(X.T, y, gpb200.MeanConst(0.2), kern, -0.5, device=local)
         gp._eng.set_option("dist_nb", dist_nb)
-        gp.init_distributed()
+        gp.init_distributed()                       # maps peer memory (fused panel broadcast) when available
         gp.update_target_and_dtarget()
+        t_p2p = (gp.mll, gp.dmll.copy())
+        gp._eng.set_option("p2p", 0)                # same problem through the NCCL panel broadcast
+        gp.update_target_and_dtarget()
+        same = abs(gp.mll - t_p2p[0]) <= 1e-12 * abs(gp.mll) and np.allclose(gp.dmll, t_p2p[1], rtol=1e-10, atol=1e-12)
+        gp._eng.set_option("p2p", 1)
+        gp.update_target_and_dtarget()
+        if not same:
+            print("MGPU p2p and nccl paths disagree", gp.mll, t_p2p[0], flush=True)
+            ok = False
         mu, s2 = gp.predict_f(Xs.T)
         if rank == 0:
             o = orc.mll_and_dmll(kern.spec(), X, y, -0.5, ("MeanConst", 0.2))

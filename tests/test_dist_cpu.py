@@ -29,7 +29,7 @@ def _worker(rank, world, port, out):
             self.args = (n, r, u)
 
     e = FakeEngine()
-    w, r = gd.init_engine_comm(e)
+    w, r = gd.init_engine_comm(e, p2p=False)
     out[rank] = (uid == bytes(range(128)), m, w, r, e.args[0], e.args[1], e.args[2] == bytes([7] * 128))
     dist.destroy_process_group()
 
