@@ -77,7 +77,11 @@ class GPE:
         import os
         from .dist import init_engine_comm
         if p2p is None:
-            p2p = os.environ.get("GPB200_P2P", "1") != "0"
+            # fused peer-memory panel push: measured faster than the NCCL broadcast at 2 GPUs, slower at 8 (the owner
+            # sends one unicast copy per peer; NCCL rides the NVSwitch) -> default on only for 2 ranks
+            import torch.distributed as tdist
+            env = os.environ.get("GPB200_P2P")
+            p2p = (env != "0") if env is not None else (tdist.is_initialized() and tdist.get_world_size() == 2)
         world, rank = init_engine_comm(self._eng, p2p=p2p)
         if world > 1:
             self.update_target()
