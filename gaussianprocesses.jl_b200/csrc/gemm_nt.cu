@@ -58,24 +58,26 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
     const int Mz = min(p.M, p.m_lim - t.zoff);
     const int Nz = min(p.N, p.n_lim - t.zoff);
     const int Kz = min(p.K, p.k_lim - t.zoff);
-    if (p.flags & GEMM_LOWER_ONLY) {
-        // lower trapezoid of an M x N tile grid (M >= N): rows 0..tn-1 triangular, rows >= tn full
+    {
+        // L2-friendly rasterisation: the tm x tn tile rectangle is walked in groups of GROUP_M tile rows,
+        // column by column inside a group, so the ~148 CTAs in flight cover ~16 rows x ~9 columns and every
+        // k-slice of an operand row panel fetched from DRAM is reused out of L2 by its neighbours (the CTAs
+        // march through k in near lock-step).  A plain row-major walk re-read the B panels once per tile.
+        // Launches whose k range starts at the tile row (GEMM_KLO_M: triangular operand) have row-dependent
+        // lengths; they walk k downwards (every tile starts at the common upper end) in narrower groups so
+        // that neighbours stay within the L2 reuse window.
+        const int GROUP_M = (p.flags & GEMM_KLO_M) ? 4 : 16;
+        const int tm = p.M / BM, tn = p.N / BN;
         const int lin = blockIdx.x;
-        const int tn = p.N / BN;
-        const int tri = tn * (tn + 1) / 2;
-        if (lin < tri) {
-            int bm = (int)((sqrt(8.0 * (double)lin + 1.0) - 1.0) * 0.5);
-            while (bm * (bm + 1) / 2 > lin) --bm;
-            while ((bm + 1) * (bm + 2) / 2 <= lin) ++bm;
-            t.bm = bm; t.bn = lin - bm * (bm + 1) / 2;
-        } else {
-            const int r = lin - tri;
-            t.bm = tn + r / tn; t.bn = r - (r / tn) * tn;
-        }
-    } else {
-        t.bn = blockIdx.x; t.bm = blockIdx.y;
+        const int per_group = GROUP_M * tn;
+        const int group = lin / per_group;
+        const int first_m = group * GROUP_M;
+        const int gsize = min(GROUP_M, tm - first_m);
+        const int in_group = lin - group * per_group;
+        t.bm = first_m + in_group % gsize;
+        t.bn = in_group / gsize;
     }
-    t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem) &&
+    t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (!(p.flags & GEMM_LOWER_ONLY) || t.bn <= t.bm) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem) &&
               (p.bn_mod <= 1 || (t.bn % p.bn_mod) == p.bn_rem);
     t.kt_lo = (p.flags & GEMM_KLO_M) ? (p.klo_off + t.bm * BM) / BK : 0;
     int hi = Kz > 0 ? Kz / BK : 0;
@@ -214,7 +216,9 @@ gpb200_dgemm_nt_tma(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const int ar = p.a_row0 + t.zoff + t.bm * BM;
             const int br = p.b_row0 + t.zoff + t.bn * BN;
             int stage = 0; uint32_t phase = 0;
-            for (int kt = t.kt_lo; kt < t.kt_hi; ++kt) {
+            const bool down = (p.flags & GEMM_KLO_M) != 0;
+            for (int it = t.kt_lo; it < t.kt_hi; ++it) {
+                const int kt = down ? (t.kt_hi - 1 - (it - t.kt_lo)) : it;
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], STAGE_BYTES);
                 unsigned char* sA = smem + stage * STAGE_BYTES;
@@ -316,12 +320,14 @@ __global__ void __launch_bounds__(SIMPLE_THREADS, 1) gpb200_dgemm_nt_simple(cons
     };
 
     if (t.kt_lo < t.kt_hi) {
-        gload(t.kt_lo);
+        const bool down = (p.flags & GEMM_KLO_M) != 0;
+        auto kmap = [&](int it) { return down ? (t.kt_hi - 1 - (it - t.kt_lo)) : it; };
+        gload(kmap(t.kt_lo));
         sstore(0);
         __syncthreads();
         int stage = 0;
         for (int kt = t.kt_lo; kt < t.kt_hi; ++kt) {
-            if (kt + 1 < t.kt_hi) gload(kt + 1);
+            if (kt + 1 < t.kt_hi) gload(kmap(kt + 1));
             const uint32_t sA = smem_base + stage * STAGE_BYTES;
             compute_stage(sA, sA + TILE_BYTES, acc, wm, wn, g, coff);
             if (kt + 1 < t.kt_hi) sstore(stage ^ 1);
@@ -385,13 +391,9 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     if (d.M <= 0 || d.N <= 0) return cudaSuccess;
     if ((d.M % BM) || (d.N % BN) || (d.K % BK)) return cudaErrorInvalidValue;
     const int tm = d.M / BM, tn = d.N / BN;
-    dim3 grid;
-    if (d.flags & GEMM_LOWER_ONLY) {
-        if (tm < tn) return cudaErrorInvalidValue;
-        grid = dim3((unsigned)(tn * (tn + 1) / 2 + (tm - tn) * tn), 1, (unsigned)d.batch);
-    } else {
-        grid = dim3((unsigned)tn, (unsigned)tm, (unsigned)d.batch);
-    }
+    if ((d.flags & GEMM_LOWER_ONLY) && tm < tn) return cudaErrorInvalidValue;
+    // one CTA per tile of the bounding rectangle (tiles above the diagonal of a LOWER_ONLY launch exit at once)
+    dim3 grid((unsigned)(tm * tn), 1, (unsigned)d.batch);
     if (impl == 0) {
         if (!d.A.buf.map || !d.B.buf.map) return cudaErrorInvalidValue;
         const CUtensorMap* ma = d.A.buf.map;
