@@ -77,7 +77,8 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
         t.bm = first_m + in_group % gsize;
         t.bn = in_group / gsize;
     }
-    t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (!(p.flags & GEMM_LOWER_ONLY) || t.bn <= t.bm) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem) &&
+    t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (!(p.flags & GEMM_LOWER_ONLY) || t.bn <= t.bm) &&
+              (!(p.flags & GEMM_SKIP_FIRST) || t.bm != 0 || t.bn != 0) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem) &&
               (p.bn_mod <= 1 || (t.bn % p.bn_mod) == p.bn_rem);
     t.kt_lo = (p.flags & GEMM_KLO_M) ? (p.klo_off + t.bm * BM) / BK : 0;
     int hi = Kz > 0 ? Kz / BK : 0;

@@ -12,6 +12,7 @@ enum : int {
     GEMM_KLO_M      = 2,   // k starts at bm*128        (A rows are upper-triangular in the frame)
     GEMM_KHI_M      = 4,   // k ends at (bm+1)*128      (A rows are lower-triangular)
     GEMM_KHI_N      = 8,   // k ends at (bn+1)*128      (B rows are lower-triangular)
+    GEMM_SKIP_FIRST = 16,  // tile (0,0) is computed elsewhere (look-ahead of the next diagonal tile)
 };
 
 // A matrix living in a handle-owned buffer.  `map` is the TMA descriptor of the whole buffer

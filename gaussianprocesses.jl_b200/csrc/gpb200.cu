@@ -77,7 +77,10 @@ struct gpb200_handle {
     // options
     int nb = 0;                 // outer Cholesky block; 0 = fully recursive (one panel)
     int gemm_impl = 0;
-    int lookahead = 0;
+    int lookahead = 1;          // factor the next diagonal tile on a side stream while the Schur update runs
+    cudaStream_t st_side = nullptr;            // high-priority stream of the look-ahead chain
+    cudaStream_t st_cur = nullptr;             // stream launch_gemm / the leaf use right now (st or st_side)
+    cudaEvent_t ev_la0 = nullptr, ev_la2 = nullptr;
     // stats
     double ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int64_t launches = 0;
@@ -257,7 +260,8 @@ double gemm_exec_flops(const GemmDesc& d) {
 cudaError_t launch_gemm(gpb200_handle* h, const GemmDesc& d) {
     ++h->launches;
     const int impl = h->tma_ok ? h->gemm_impl : 1;
-    if (!h->profile) return gemm_nt_launch(d, impl, h->st);
+    cudaStream_t stc = h->st_cur ? h->st_cur : h->st;
+    if (!h->profile || stc != h->st) return gemm_nt_launch(d, impl, stc);
     if (h->pev_used + 2 > h->pev.size()) {
         const size_t old = h->pev.size();
         h->pev.resize(old + 512);
@@ -302,14 +306,14 @@ cudaError_t panel_trsm_leaf(gpb200_handle* h, int r0, int rows, int p) {
 }
 // Schur update of the lower trapezoid G[r0.., r0..r0+cols) -= F[r0.., p..p+k) F[r0..r0+cols, p..p+k)'
 // (rows >= cols; cols == rows gives the classical trailing SYRK)
-cudaError_t schur_update(gpb200_handle* h, int r0, int rows, int cols, int p, int k) {
+cudaError_t schur_update(gpb200_handle* h, int r0, int rows, int cols, int p, int k, int extra_flags = 0) {
     GemmDesc g = gemm_desc_default();
     g.A = GemmOperand{bufF(h), bufNone(), r0, p};
     g.B = GemmOperand{bufF(h), bufNone(), r0, p};
     g.C = h->G; g.ldc = h->ld; g.c_row0 = r0; g.c_col0 = r0;
     g.M = rows; g.N = cols; g.K = k;
     g.alpha = -1.0; g.beta = 1.0;
-    g.flags = GEMM_LOWER_ONLY;
+    g.flags = GEMM_LOWER_ONLY | extra_flags;
     return launch_gemm(h, g);
 }
 // merge of the inverses of two adjacent diagonal blocks [p,p+n1) and [p+n1,p+n1+n2):
@@ -349,26 +353,48 @@ cudaError_t merge_inverse(gpb200_handle* h, int p, int n1, int n2, int batch) {
 // p aligned to s).  Every Schur update inside is one NT GEMM whose inner dimension is the half
 // block size, so ~98% of the flops run with K >= 1024 (near-peak DMMA activity); only the
 // 128-wide leaves (tile factorisation + TRSM through the inverted tile) are latency bound.
-cudaError_t chol_panel(gpb200_handle* h, int p, int n, int s) {
+cudaError_t leaf_launch(gpb200_handle* h, int p, cudaStream_t st) {
+    ++h->launches;
+    PotrfPeers pp{};
+    if (h->push_panel) {
+        pp.n = h->n_peer;
+        for (int q = 0; q < h->n_peer; ++q) { pp.F[q] = h->peer_F[q]; pp.Dinv[q] = h->peer_Dinv[q]; pp.DinvT[q] = h->peer_DinvT[q]; pp.logd[q] = h->peer_logd[q]; }
+    }
+    return potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, st, &pp);
+}
+
+// `leaf_done`: the tile at p was already factored by the look-ahead chain on the side stream (join it first).
+// Look-ahead: once the left half of a node is done, the ONE tile of the Schur update the next leaf needs and
+// that leaf run on a high-priority side stream while the main stream does the rest of the update -- the
+// 125 us latency-bound leaf disappears behind the GEMM.
+cudaError_t chol_panel(gpb200_handle* h, int p, int n, int s, bool leaf_done = false) {
     const int Np = (int)h->Npad;
     cudaError_t e;
     if (s == TILE) {
-        ++h->launches;
-        PotrfPeers pp{};
-        if (h->push_panel) {
-            pp.n = h->n_peer;
-            for (int q = 0; q < h->n_peer; ++q) { pp.F[q] = h->peer_F[q]; pp.Dinv[q] = h->peer_Dinv[q]; pp.DinvT[q] = h->peer_DinvT[q]; pp.logd[q] = h->peer_logd[q]; }
-        }
-        e = potrf128_launch(h->G, h->ld, h->F, h->ld, h->Dinv, h->DinvT, h->logd, h->info_dev, p, 1, TILE, h->st, &pp);
+        if (leaf_done) e = cudaStreamWaitEvent(h->st, h->ev_la2, 0);
+        else e = leaf_launch(h, p, h->st);
         if (e != cudaSuccess) return e;
         const int below = Np - p - TILE;
         return below > 0 ? panel_trsm_leaf(h, p + TILE, below, p) : cudaSuccess;
     }
     const int hs = s / 2;
-    if (n <= hs) return chol_panel(h, p, n, hs);
-    if ((e = chol_panel(h, p, hs, hs)) != cudaSuccess) return e;
-    if ((e = schur_update(h, p + hs, Np - p - hs, n - hs, p, hs)) != cudaSuccess) return e;
-    return chol_panel(h, p + hs, n - hs, hs);
+    if (n <= hs) return chol_panel(h, p, n, hs, leaf_done);
+    if ((e = chol_panel(h, p, hs, hs, leaf_done)) != cudaSuccess) return e;
+    const int rows = Np - p - hs, cols = n - hs;
+    if (h->lookahead && h->st_side) {
+        if ((e = cudaEventRecord(h->ev_la0, h->st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(h->st_side, h->ev_la0, 0)) != cudaSuccess) return e;
+        h->st_cur = h->st_side;
+        e = schur_update(h, p + hs, TILE, TILE, p, hs);                 // the next diagonal tile only
+        h->st_cur = nullptr;
+        if (e != cudaSuccess) return e;
+        if ((e = leaf_launch(h, p + hs, h->st_side)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(h->ev_la2, h->st_side)) != cudaSuccess) return e;
+        if ((e = schur_update(h, p + hs, rows, cols, p, hs, GEMM_SKIP_FIRST)) != cudaSuccess) return e;
+        return chol_panel(h, p + hs, cols, hs, true);
+    }
+    if ((e = schur_update(h, p + hs, rows, cols, p, hs)) != cudaSuccess) return e;
+    return chol_panel(h, p + hs, cols, hs);
 }
 
 cudaError_t cholesky(gpb200_handle* h) {
@@ -879,6 +905,13 @@ int gpb200_create(gpb200_handle** out, int device) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->st_side, cudaStreamNonBlocking, hi) != cudaSuccess) { h->st_side = nullptr; (void)cudaGetLastError(); }
+        cudaEventCreateWithFlags(&h->ev_la0, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_la2, cudaEventDisableTiming);
+    }
     if ((e = gemm_nt_init()) != cudaSuccess) return bail("gemm_nt_init", e);
     const char* env = getenv("GPB200_GEMM");
     if (env) h->gemm_impl = atoi(env);
@@ -899,6 +932,9 @@ void gpb200_destroy(gpb200_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->ev_la0) cudaEventDestroy(h->ev_la0);
+    if (h->ev_la2) cudaEventDestroy(h->ev_la2);
+    if (h->st_side) cudaStreamDestroy(h->st_side);
     for (auto e : h->pev) cudaEventDestroy(e);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int i = 0; i < 2; ++i) {
