@@ -68,14 +68,39 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
         // that neighbours stay within the L2 reuse window.
         const int GROUP_M = (p.flags & GEMM_KLO_M) ? 4 : 16;
         const int tm = p.M / BM, tn = p.N / BN;
-        const int lin = blockIdx.x;
-        const int per_group = GROUP_M * tn;
-        const int group = lin / per_group;
-        const int first_m = group * GROUP_M;
-        const int gsize = min(GROUP_M, tm - first_m);
-        const int in_group = lin - group * per_group;
-        t.bm = first_m + in_group % gsize;
-        t.bn = in_group / gsize;
+        int rem = blockIdx.x;
+        if (!(p.flags & GEMM_LOWER_ONLY)) {
+            const int per_group = GROUP_M * tn;
+            const int group = rem / per_group;
+            const int first_m = group * GROUP_M;
+            const int gsize = min(GROUP_M, tm - first_m);
+            const int in_group = rem - group * per_group;
+            t.bm = first_m + in_group % gsize;
+            t.bn = in_group / gsize;
+        } else {
+            // lower trapezoid (tm >= tn): only tiles bn <= bm exist; same grouped walk, compactly enumerated
+            int first_m = 0, gsize = 0;
+            for (;;) {
+                gsize = min(GROUP_M, tm - first_m);
+                int cnt = 0;
+                for (int r = first_m; r < first_m + gsize; ++r) cnt += min(r, tn - 1) + 1;
+                if (rem < cnt || first_m + gsize >= tm) break;
+                rem -= cnt; first_m += gsize;
+            }
+            const int full_cols = min(first_m, tn);             // columns every row of the group owns
+            if (rem < full_cols * gsize) {
+                t.bn = rem / gsize; t.bm = first_m + rem % gsize;
+            } else {
+                rem -= full_cols * gsize;
+                int bn = full_cols;
+                for (;;) {                                       // diagonal part of the group: rows >= bn
+                    const int nrows = first_m + gsize - max(bn, first_m);
+                    if (rem < nrows || bn + 1 >= tn) break;
+                    rem -= nrows; ++bn;
+                }
+                t.bn = bn; t.bm = max(bn, first_m) + rem;
+            }
+        }
     }
     t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (!(p.flags & GEMM_LOWER_ONLY) || t.bn <= t.bm) &&
               (!(p.flags & GEMM_SKIP_FIRST) || t.bm != 0 || t.bn != 0) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem) &&
@@ -393,8 +418,10 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     if ((d.M % BM) || (d.N % BN) || (d.K % BK)) return cudaErrorInvalidValue;
     const int tm = d.M / BM, tn = d.N / BN;
     if ((d.flags & GEMM_LOWER_ONLY) && tm < tn) return cudaErrorInvalidValue;
-    // one CTA per tile of the bounding rectangle (tiles above the diagonal of a LOWER_ONLY launch exit at once)
-    dim3 grid((unsigned)(tm * tn), 1, (unsigned)d.batch);
+    // one CTA per tile (LOWER_ONLY: per tile of the lower trapezoid), walked in L2-friendly groups
+    long long ntiles = (long long)tm * tn;
+    if (d.flags & GEMM_LOWER_ONLY) { ntiles = 0; for (int r = 0; r < tm; ++r) ntiles += (r < tn - 1 ? r : tn - 1) + 1; }
+    dim3 grid((unsigned)ntiles, 1, (unsigned)d.batch);
     if (impl == 0) {
         if (!d.A.buf.map || !d.B.buf.map) return cudaErrorInvalidValue;
         const CUtensorMap* ma = d.A.buf.map;

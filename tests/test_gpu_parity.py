@@ -204,3 +204,41 @@ def test_gpe_mirror_end_to_end(engine):
         gp.predict_f(np.zeros((3, 5)))
     my, sy = gp.predict_y(X.T[:, :5])
     assert np.allclose(sy, s2[:5] + gp.noise_variance())
+
+
+def test_engine_stream_profile_and_options(engine):
+    """set_stream (caller-owned CUDA stream), per-launch GEMM profiling counters, option validation, FP64 peak probe."""
+    import torch
+    import gpb200
+    X, y, _ = make_data(900, 3, 77)
+    k = gpb200.SEIso(0.2, 0.1)
+    theta, _ = _setup(engine, k, X, nb=0, gemm=0)
+    o = orc.fit(k.spec(), X, y, -0.5)
+    s = torch.cuda.Stream()
+    engine.set_stream(s.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    engine.set_option("profile", 1)
+    e0.record(s)
+    engine.factorize(theta, -0.5)
+    alpha, mll = engine.mll(y)
+    engine.grad_prepare()
+    e1.record(s)
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) > 0.0
+    assert abs(mll - o["mll"]) <= RTOL * abs(o["mll"])
+    t = engine.timings()
+    assert t["gemm_launches"] > 0 and t["gemm_ms"] > 0 and t["gemm_flops"] > 2.0 * 900 ** 3 / 3
+    engine.set_option("profile", 0)
+    engine.set_stream(0)
+    for lookahead in (0, 1):                                   # both schedules give the same factor bit for bit
+        engine.set_option("lookahead", lookahead)
+        engine.factorize(theta, -0.5)
+        a2, m2 = engine.mll(y)
+        assert m2 == mll and np.array_equal(a2, alpha)
+    with pytest.raises(ValueError):
+        engine.set_option("nb", 300)
+    with pytest.raises(ValueError):
+        engine.set_option("no_such_option", 1)
+    pk = engine.fp64_peak()
+    assert 5.0 < pk["dmma_tflops"] < 80.0 and 5.0 < pk["dfma_tflops"] < 80.0
+    assert engine.launch_count() > 0
