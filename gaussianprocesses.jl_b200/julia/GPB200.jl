@@ -183,6 +183,102 @@ function predictMVN(xpred::AbstractMatrix, xtrain, ytrain, kernel::Kernel, meanf
     error("predictMVN(B200Covariance) is reached through predict_f(gp, x); call that instead")
 end
 
-export B200Covariance
+# =====================================================================================================
+# Sparse strategies on the device: FITC / DTC / SoR (src/sparse/*.jl) -> gpb200_fitc_* (one streaming engine)
+#     gp = GPE(x, y, mean, kernel, logNoise, B200Sparse(Xu, :FITC))
+# =====================================================================================================
+import GaussianProcesses: SparseStrategy
+
+struct B200Sparse{M<:AbstractMatrix} <: SparseStrategy
+    inducing::M
+    mode::Symbol              # :FITC (fully_indep_train_conditional.jl), :DTC (determ_train_conditional.jl), :SoR
+    device::Int
+end
+B200Sparse(Xu::AbstractMatrix, mode::Symbol=:FITC) = B200Sparse(Xu, mode, 0)
+const SPARSE_MODE = Dict(:FITC => 0, :DTC => 1, :SoR => 2)
+
+mutable struct B200SparsePDMat <: AbstractPDMat{Float64}
+    handle::Ptr{Cvoid}
+    n::Int
+    exposed::Vector{Int}
+    alpha::Vector{Float64}     # Sigma^-1 r of the last `\`
+    logdet::Float64
+    function B200SparsePDMat(cs::B200Sparse, n::Int)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:gpb200_fitc_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, cs.device)
+        rc == 0 || error("gpb200_fitc_create failed ($rc)")
+        ccall((:gpb200_fitc_set_mode, LIB), Cint, (Ptr{Cvoid}, Cint), h[], SPARSE_MODE[cs.mode])
+        obj = new(h[], n, Int[], Float64[], NaN)
+        finalizer(o -> ccall((:gpb200_fitc_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle), obj)
+        return obj
+    end
+end
+size(a::B200SparsePDMat) = (a.n, a.n)
+dim(a::B200SparsePDMat) = a.n
+
+function checks(cK::B200SparsePDMat, rc::Integer, what)
+    rc == 0 && return
+    rc > 0 && throw(PosDefException(rc))
+    msg = unsafe_string(ccall((:gpb200_fitc_last_error, LIB), Cstring, (Ptr{Cvoid},), cK.handle))
+    (rc == -1 || rc == -4) && throw(ArgumentError("$what: $msg"))
+    error("$what failed ($rc): $msg")
+end
+
+KernelData(k::Kernel, X1::AbstractMatrix, X2::AbstractMatrix, ::B200Sparse) = EmptyData()
+alloc_cK(cs::B200Sparse, nobs) = B200SparsePDMat(cs, nobs)
+
+# update_cK!(::FullyIndepPDMat) fitc.jl:134-156 / update_cK!(::SubsetOfRegsPDMat) sor.jl:96-106
+function update_cK!(cK::B200SparsePDMat, x::AbstractMatrix, kernel::Kernel, logNoise::Real, data::KernelData, cs::B200Sparse)
+    X = Matrix{Float64}(x); Xu = Matrix{Float64}(cs.inducing)
+    d, n = size(X)
+    checks(cK, ccall((:gpb200_fitc_set_data, LIB), Cint,
+                     (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64),
+                     cK.handle, n, d, X, d, size(Xu, 2), Xu, d), "fitc_set_data")
+    ops, dims, theta, exposed = flatten(kernel, d)
+    cK.exposed = exposed
+    checks(cK, ccall((:gpb200_fitc_set_kernel, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32),
+                     cK.handle, length(ops) ÷ 6, ops, length(dims), dims, length(theta)), "fitc_set_kernel")
+    checks(cK, ccall((:gpb200_fitc_factorize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64),
+                     cK.handle, theta, Float64(logNoise)), "fitc_factorize")
+    return cK
+end
+
+# `\` (fitc.jl:33-36, sor.jl:50) and logdet (fitc.jl:77, sor.jl:53) come from one device pass
+function \(cK::B200SparsePDMat, y::AbstractVector)
+    alpha = Vector{Float64}(undef, cK.n); mll = Ref{Float64}(0.0); ld = Ref{Float64}(0.0)
+    checks(cK, ccall((:gpb200_fitc_mll, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
+                     cK.handle, Vector{Float64}(y), alpha, mll, ld), "fitc_mll")
+    cK.alpha = alpha; cK.logdet = ld[]
+    return alpha
+end
+logdet(cK::B200SparsePDMat) = cK.logdet
+
+struct B200SparsePrecompute <: AbstractGradientPrecompute end
+init_precompute(::B200Sparse, X, y, k) = B200SparsePrecompute()
+precompute!(::B200SparsePrecompute, gp) = nothing
+
+function dmll_noise(gp::GPE, ::B200SparsePrecompute, ::B200Sparse)                 # fitc.jl:243-257, sor.jl:159-166
+    g = Ref{Float64}(0.0)
+    checks(gp.cK, ccall((:gpb200_fitc_grad_noise, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}), gp.cK.handle, g), "fitc_grad_noise")
+    return g[]
+end
+function dmll_kern!(dmll::AbstractVector, gp, ::B200SparsePrecompute, ::B200Sparse)    # fitc.jl:200-234, sor.jl:219-253
+    nfull = maximum(gp.cK.exposed; init=0)
+    g = Vector{Float64}(undef, max(nfull, 1))
+    checks(gp.cK, ccall((:gpb200_fitc_grad_kernel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), gp.cK.handle, g), "fitc_grad_kernel")
+    dmll .= g[gp.cK.exposed]
+    return dmll
+end
+function predict_f(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractMatrix; full_cov::Bool=false) where {X,Y,M,K,CS<:B200Sparse,D,P}
+    full_cov && throw(ArgumentError("B200Sparse: full predictive covariance is not built; use full_cov=false"))
+    size(x, 1) == gp.dim || throw(ArgumentError("Gaussian Process object and input observations do not have consistent dimensions"))
+    Xs = Matrix{Float64}(x); Ms = size(Xs, 2)
+    mu = Vector{Float64}(undef, Ms); var = Vector{Float64}(undef, Ms)
+    checks(gp.cK, ccall((:gpb200_fitc_predict, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                        gp.cK.handle, Ms, Xs, size(Xs, 1), mu, var), "fitc_predict")
+    return mu .+ mean(gp.mean, Xs), max.(var, 0.0)
+end
+
+export B200Covariance, B200Sparse
 
 end # module
