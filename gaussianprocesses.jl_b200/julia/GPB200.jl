@@ -40,11 +40,12 @@ mutable struct B200PDMat <: AbstractPDMat{Float64}
     handle::Ptr{Cvoid}
     n::Int
     exposed::Vector{Int}          # positions of get_params(kernel) inside the device's full theta
+    ntheta::Int                   # length of the device's full parameter vector (FixedKernel may hide some)
     function B200PDMat(device::Int, n::Int)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:gpb200_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
         rc == 0 || error("gpb200_create: ", unsafe_string(ccall((:gpb200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
-        obj = new(h[], n, Int[])
+        obj = new(h[], n, Int[], 0)
         finalizer(o -> ccall((:gpb200_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle), obj)
         return obj
     end
@@ -105,7 +106,7 @@ function update_cK!(cK::B200PDMat, x::AbstractMatrix, kernel::Kernel, logNoise, 
     d, n = size(X)
     check(cK, ccall((:gpb200_set_data, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64), cK.handle, n, d, X, d), "set_data")
     ops, dims, theta, exposed = flatten(kernel, d)
-    cK.exposed = exposed
+    cK.exposed = exposed; cK.ntheta = length(theta)
     check(cK, ccall((:gpb200_set_kernel, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32),
                     cK.handle, length(ops) ÷ 6, ops, length(dims), dims, length(theta)), "set_kernel")
     ln = Float64.(vcat(logNoise))                # Scalar or VectorParam (src/GPE.jl:169 vs :177)
@@ -141,8 +142,7 @@ function precompute!(pre::B200Precompute, gp)                                   
 end
 
 function grad_full(pre::B200Precompute, gp)
-    nfull = maximum(pre.cK.exposed; init=0)
-    g = Vector{Float64}(undef, max(nfull, 1)); trA = Ref{Float64}(0.0)
+    g = Vector{Float64}(undef, max(pre.cK.ntheta, 1)); trA = Ref{Float64}(0.0)
     check(pre.cK, ccall((:gpb200_grad_kernel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
                         pre.cK.handle, gp.alpha, g, trA), "grad_kernel")
     return g, trA[]
@@ -208,7 +208,7 @@ mutable struct B200SparsePDMat <: AbstractPDMat{Float64}
         rc = ccall((:gpb200_fitc_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, cs.device)
         rc == 0 || error("gpb200_fitc_create failed ($rc)")
         ccall((:gpb200_fitc_set_mode, LIB), Cint, (Ptr{Cvoid}, Cint), h[], SPARSE_MODE[cs.mode])
-        obj = new(h[], n, Int[], Float64[], NaN)
+        obj = new(h[], n, Int[], 0, Float64[], NaN)
         finalizer(o -> ccall((:gpb200_fitc_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle), obj)
         return obj
     end
@@ -235,7 +235,7 @@ function update_cK!(cK::B200SparsePDMat, x::AbstractMatrix, kernel::Kernel, logN
                      (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64),
                      cK.handle, n, d, X, d, size(Xu, 2), Xu, d), "fitc_set_data")
     ops, dims, theta, exposed = flatten(kernel, d)
-    cK.exposed = exposed
+    cK.exposed = exposed; cK.ntheta = length(theta)
     checks(cK, ccall((:gpb200_fitc_set_kernel, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32),
                      cK.handle, length(ops) ÷ 6, ops, length(dims), dims, length(theta)), "fitc_set_kernel")
     checks(cK, ccall((:gpb200_fitc_factorize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64),
@@ -263,8 +263,7 @@ function dmll_noise(gp::GPE, ::B200SparsePrecompute, ::B200Sparse)              
     return g[]
 end
 function dmll_kern!(dmll::AbstractVector, gp, ::B200SparsePrecompute, ::B200Sparse)    # fitc.jl:200-234, sor.jl:219-253
-    nfull = maximum(gp.cK.exposed; init=0)
-    g = Vector{Float64}(undef, max(nfull, 1))
+    g = Vector{Float64}(undef, max(gp.cK.ntheta, 1))
     checks(gp.cK, ccall((:gpb200_fitc_grad_kernel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), gp.cK.handle, g), "fitc_grad_kernel")
     dmll .= g[gp.cK.exposed]
     return dmll
