@@ -135,8 +135,15 @@ int  gpb200_get_inverse(gpb200_handle* h, double* Kinv);  /* N x N, after gpb200
 int  gpb200_get_timings(gpb200_handle* h, double* ms, int32_t n);
 /* number of kernel launches issued by this handle since creation */
 int64_t gpb200_launch_count(gpb200_handle* h);
-/* tuning knobs (string key): "nb" outer Cholesky block, "gemm" 0=TMA kernel 1=simple kernel,
- * "lookahead" 0/1, "profile" 0/1.  Returns GPB200_EINVAL for unknown keys.                    */
+/* tuning knobs (string key):
+ *   "nb"         outer Cholesky block: 0 (default) = fully recursive, else 128*2^k <= 4096 (right-looking panels)
+ *   "gemm"       0 = TMA/mbarrier DMMA kernel (default), 1 = simple-loader kernel (bring-up / cross-check)
+ *   "lookahead"  1 (default) = next diagonal tile factored on a side stream behind the Schur update
+ *   "trsv_fused" 1 (default) = single-launch flag-synchronised triangular solves, 0 = one launch per block step
+ *   "profile"    1 = CUDA events around every GEMM launch (see gpb200_get_timings)
+ *   "dist_nb"    multi-GPU: width of an owned block column, 0 = auto (~N/(8*ranks))
+ *   "p2p"        multi-GPU: 1 = fused panel push over peer memory (after gpb200_ipc_import), 0 = NCCL broadcast
+ * Returns GPB200_EINVAL for unknown keys or values.                                           */
 int  gpb200_set_option(gpb200_handle* h, const char* key, int64_t value);
 
 /* run all work of this handle on the caller's CUDA stream (cudaStream_t; NULL = a private
