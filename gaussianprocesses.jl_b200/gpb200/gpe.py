@@ -77,11 +77,11 @@ class GPE:
         import os
         from .dist import init_engine_comm
         if p2p is None:
-            # fused peer-memory panel push: measured faster than the NCCL broadcast at 2 GPUs, slower at 8 (the owner
-            # sends one unicast copy per peer; NCCL rides the NVSwitch) -> default on only for 2 ranks
+            # fused peer-memory panel push: measured faster than the NCCL broadcast at 2 and 4 GPUs, slower at 8 (the
+            # owner sends one unicast copy per peer; NCCL rides the NVSwitch) -> default on up to 4 ranks
             import torch.distributed as tdist
             env = os.environ.get("GPB200_P2P")
-            p2p = (env != "0") if env is not None else (tdist.is_initialized() and tdist.get_world_size() == 2)
+            p2p = (env != "0") if env is not None else (tdist.is_initialized() and tdist.get_world_size() <= 4)
         world, rank = init_engine_comm(self._eng, p2p=p2p)
         if world > 1:
             self.update_target()
