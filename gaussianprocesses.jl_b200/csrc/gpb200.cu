@@ -1275,6 +1275,10 @@ int gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, 
     }
     // chunk the test points so that the M_c x Npad workspace stays below ~16 GB
     int64_t cap = (int64_t)(16.0e9 / (8.0 * (double)h->Npad)) / TILE * TILE;
+    if (const char* env = getenv("GPB200_PREDICT_CHUNK")) {            // testing hook: force small chunks
+        const int64_t v = atoll(env) / TILE * TILE;
+        if (v >= TILE && v < cap) cap = v;
+    }
     if (cap < TILE) cap = TILE;
     if (cov) cap = (M + TILE - 1) / TILE * TILE;          // full covariance needs all of V at once
     const bool need_v = (var != nullptr) || (cov != nullptr);

@@ -242,3 +242,23 @@ def test_engine_stream_profile_and_options(engine):
     pk = engine.fp64_peak()
     assert 5.0 < pk["dmma_tflops"] < 80.0 and 5.0 < pk["dfma_tflops"] < 80.0
     assert engine.launch_count() > 0
+
+
+def test_predict_chunking_and_explicit_alpha(engine, monkeypatch):
+    """Many test points are streamed through the cross-Gram workspace in chunks; alpha may be passed explicitly."""
+    import gpb200
+    X, y, _ = make_data(700, 3, 13)
+    Xs = np.random.default_rng(14).standard_normal((1000, 3))
+    k = gpb200.Mat52Iso(0.1, 0.2)
+    theta, _ = _setup(engine, k, X, nb=0, gemm=0)
+    engine.factorize(theta, -0.7)
+    alpha, _ = engine.mll(y)
+    o = orc.fit(k.spec(), X, y, -0.7)
+    mo, vo = orc.predict_f(k.spec(), X, o, Xs)
+    monkeypatch.setenv("GPB200_PREDICT_CHUNK", "256")              # 4 chunks of 256 rows
+    mu, var, _ = engine.predict(Xs, alpha=o["alpha"])
+    assert _rel(mu, mo) < RTOL
+    assert np.max(np.abs(var - vo)) <= RTOL * np.max(np.abs(vo)) + 1e-13
+    monkeypatch.delenv("GPB200_PREDICT_CHUNK")
+    mu1, var1, _ = engine.predict(Xs)                              # single chunk, resident alpha
+    assert np.allclose(mu1, mu, rtol=0, atol=1e-12 * np.max(np.abs(mu))) and np.allclose(var1, var, rtol=0, atol=1e-12)
