@@ -169,6 +169,16 @@ class GPE:
             return mu, s2 + nv * np.eye(s2.shape[0])
         return mu, s2 + nv
 
+    def rand(self, x, n=1, nugget=1e-10, rng=None):
+        """rand(gp, X, n) (src/GP.jl:120-146): n posterior draws at the columns of x.  The M x M predictive
+        covariance comes from the device (predict_f full_cov), its small Cholesky and the normal draws stay
+        on the host exactly like the reference's make_posdef! + unwhiten!."""
+        rng = np.random.default_rng() if rng is None else rng
+        mu, Sigma = self.predict_f(x, full_cov=True)
+        Sigma = Sigma + nugget * np.eye(Sigma.shape[0])                  # make_posdef!(Σraw; nugget)
+        L = np.linalg.cholesky(Sigma)
+        return mu[:, None] + L @ rng.standard_normal((mu.size, int(n)))
+
     # ---- parameters ----------------------------------------------------------------------
     def get_params(self, noise=True, domean=True, kern=True):      # GPE.jl:447-458
         p = []

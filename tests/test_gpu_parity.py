@@ -204,6 +204,12 @@ def test_gpe_mirror_end_to_end(engine):
         gp.predict_f(np.zeros((3, 5)))
     my, sy = gp.predict_y(X.T[:, :5])
     assert np.allclose(sy, s2[:5] + gp.noise_variance())
+    # rand(gp, X, n) (test/gp.jl: posterior samples): right shape, sample mean -> predictive mean
+    Xq = X.T[:, :6] + 0.05
+    draws = gp.rand(Xq, 4000, rng=np.random.default_rng(0))
+    mq, cq = gp.predict_f(Xq, full_cov=True)
+    assert draws.shape == (6, 4000)
+    assert np.max(np.abs(draws.mean(axis=1) - mq)) < 5 * np.sqrt(np.max(np.diag(cq)) / 4000) + 1e-6
 
 
 def test_engine_stream_profile_and_options(engine):
