@@ -1374,6 +1374,18 @@ int gpb200_get_inverse(gpb200_handle* h, double* Kinv) {
     return GPB200_OK;
 }
 
+int gpb200_get_inverse_diag(gpb200_handle* h, double* diag) {
+    if (!h || !diag) return GPB200_EINVAL;
+    if (!h->inv_ready) return fail(h, GPB200_ESTATE, "get_inverse_diag: grad_prepare first");
+    if (h->nranks > 1) return fail(h, GPB200_ESTATE, "get_inverse_diag: K^-1 is distributed over the ranks (tile rows round-robin)");
+    CK(cudaSetDevice(h->device));
+    // strided gather of G[i,i]: pitch (ld+1) doubles, one double per row
+    CK(cudaMemcpy2DAsync(diag, sizeof(double), h->G, sizeof(double) * (h->ld + 1), sizeof(double), h->N,
+                         cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return GPB200_OK;
+}
+
 int gpb200_dgemm_nt_device(gpb200_handle* h, int impl, int64_t M, int64_t N, int64_t K, double alpha,
                            const double* dA, int64_t lda, const double* dB, int64_t ldb, double beta, double* dC,
                            int64_t ldc, int lower_only, int reps, double* ms) {

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "gpb200_get_gram": (C.c_int, [_H, _dp]),
     "gpb200_get_factor": (C.c_int, [_H, _dp]),
     "gpb200_get_inverse": (C.c_int, [_H, _dp]),
+    "gpb200_get_inverse_diag": (C.c_int, [_H, _dp]),
     "gpb200_get_timings": (C.c_int, [_H, _dp, C.c_int32]),
     "gpb200_launch_count": (C.c_int64, [_H]),
     "gpb200_set_option": (C.c_int, [_H, C.c_char_p, C.c_int64]),
@@ -227,6 +228,11 @@ class Engine:
         K = np.empty((self.N, self.N))
         self._check(self._lib.gpb200_get_inverse(self._h, _as_dp(K)), "get_inverse")
         return K
+
+    def inverse_diag(self):
+        d = np.empty(self.N)
+        self._check(self._lib.gpb200_get_inverse_diag(self._h, _as_dp(d)), "get_inverse_diag")
+        return d
 
     def timings(self):
         ms = np.zeros(12)

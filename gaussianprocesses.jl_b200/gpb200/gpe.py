@@ -169,6 +169,17 @@ class GPE:
             return mu, s2 + nv * np.eye(s2.shape[0])
         return mu, s2 + nv
 
+    def predict_LOO(self):
+        """predict_LOO(gp) (src/crossvalidation.jl:8-36): leave-one-out means / variances from diag(K_y^-1) and alpha."""
+        self._eng.grad_prepare()
+        s2 = 1.0 / self._eng.inverse_diag()
+        return -self.alpha * s2 + self.y, s2
+
+    def logp_LOO(self):
+        """logp_LOO(gp) (src/crossvalidation.jl:37-49): sum of Normal log-pdfs of y_i under the LOO predictions."""
+        mu, s2 = self.predict_LOO()
+        return float(np.sum(-0.5 * np.log(2.0 * np.pi * s2) - 0.5 * (self.y - mu) ** 2 / s2))
+
     def rand(self, x, n=1, nugget=1e-10, rng=None):
         """rand(gp, X, n) (src/GP.jl:120-146): n posterior draws at the columns of x.  The M x M predictive
         covariance comes from the device (predict_f full_cov), its small Cholesky and the normal draws stay

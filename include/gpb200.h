@@ -127,6 +127,9 @@ int  gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs,
 int  gpb200_get_gram(gpb200_handle* h, double* K);        /* N x N, K_y rebuilt from x, theta   */
 int  gpb200_get_factor(gpb200_handle* h, double* U);      /* N x N column-major upper U, K_y=U'U */
 int  gpb200_get_inverse(gpb200_handle* h, double* Kinv);  /* N x N, after gpb200_grad_prepare    */
+/* diag(K_y^-1)[N] after gpb200_grad_prepare: all predict_LOO / logp_LOO need besides alpha
+ * (src/crossvalidation.jl:8-13, 37-49: sigma_i^2 = 1/[K^-1]_ii, mu_i = y_i - alpha_i sigma_i^2)  */
+int  gpb200_get_inverse_diag(gpb200_handle* h, double* diag);
 /* per-phase device times (ms) of the last calls:
  * [0] gram  [1] cholesky  [2] solve+mll  [3] inverse (trtri+lauum)  [4] trace  [5] predict
  * with option "profile"=1, accumulated since the option was set:

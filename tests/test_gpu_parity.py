@@ -204,6 +204,17 @@ def test_gpe_mirror_end_to_end(engine):
         gp.predict_f(np.zeros((3, 5)))
     my, sy = gp.predict_y(X.T[:, :5])
     assert np.allclose(sy, s2[:5] + gp.noise_variance())
+    # LOO predictions (test/test_crossvalidation.jl: analytic LOO == refit without point i)
+    mu_loo, s2_loo = gp.predict_LOO()
+    Kinv = np.linalg.inv(orc.gram(gp.kernel.spec(), X, gp.logNoise))
+    r = y - gp.mean.mean(X)
+    assert np.allclose(s2_loo, 1.0 / np.diag(Kinv), rtol=1e-8)
+    assert np.allclose(mu_loo, y - (Kinv @ r) / np.diag(Kinv), rtol=1e-7, atol=1e-9)
+    keep = np.arange(200) != 17
+    f17 = orc.fit(gp.kernel.spec(), X[keep], y[keep], gp.logNoise, gp.mean.spec())
+    m17, v17 = orc.predict_f(gp.kernel.spec(), X[keep], f17, X[17:18], gp.mean.spec())
+    assert abs(mu_loo[17] - m17[0]) < 1e-7 and abs(s2_loo[17] - (v17[0] + gp.noise_variance())) < 1e-7
+    assert np.isfinite(gp.logp_LOO())
     # rand(gp, X, n) (test/gp.jl: posterior samples): right shape, sample mean -> predictive mean
     Xq = X.T[:, :6] + 0.05
     draws = gp.rand(Xq, 4000, rng=np.random.default_rng(0))
