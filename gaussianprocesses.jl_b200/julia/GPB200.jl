@@ -159,6 +159,15 @@ function dmll_noise(gp::GPE, pre::B200Precompute, ::B200Covariance)             
     return exp(2 * GaussianProcesses.get_value(gp.logNoise)) * trA
 end
 
+# leave-one-out predictions (src/crossvalidation.jl:8-13) without materialising inv(Σ) on the host
+function GaussianProcesses.predict_LOO(cK::B200PDMat, alpha::AbstractVector{<:Real}, y::AbstractVector{<:Real})
+    check(cK, ccall((:gpb200_grad_prepare, LIB), Cint, (Ptr{Cvoid},), cK.handle), "grad_prepare")
+    d = Vector{Float64}(undef, cK.n)
+    check(cK, ccall((:gpb200_get_inverse_diag, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), cK.handle, d), "get_inverse_diag")
+    σi2 = 1 ./ d
+    return -alpha .* σi2 .+ y, σi2
+end
+
 # batched prediction instead of the per-column loop of src/GP.jl:72-76
 function predict_raw(gp::GPE, x::AbstractMatrix, full_cov::Bool)
     size(x, 1) == gp.dim || throw(ArgumentError("Gaussian Process object and input observations do not have consistent dimensions"))
