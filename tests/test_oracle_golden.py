@@ -94,3 +94,25 @@ def test_oracle_fitc_matches_dense_formulation():
     fd = (orc.fitc_fit(spec, X, Xu, y, -1.0 + e, ("MeanConst", 0.1))["mll"]
           - orc.fitc_fit(spec, X, Xu, y, -1.0 - e, ("MeanConst", 0.1))["mll"]) / (2 * e)
     assert abs(fd - f["dmll_noise"]) < 1e-3 * abs(fd)          # :134-144 (atol 1e-3 there)
+
+
+@pytest.mark.parametrize("mode", ["FITC", "SoR", "DTC"])
+def test_oracle_sparse_gradients_vs_finite_differences(mode):
+    """test/test_sparse.jl:134-144 for every sparse strategy: the literal restatement of dmll_kern! / dmll_noise
+    against finite differences of the sparse mll."""
+    rng = np.random.default_rng(1)
+    N, M, d = 250, 20, 2
+    X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    th = [-0.6, 0.1, -0.4, -0.3, 0.2]
+    mk = lambda t: ("Sum", ("SEIso", list(t[:2])), ("RQIso", list(t[2:])))
+    f = orc.fitc_fit(mk(th), X, Xu, y, -1.0, mode=mode)
+    g = orc.fitc_dmll_kern(mk(th), X, Xu, f)
+    e = 1e-5
+    for p in range(len(th)):
+        tp, tm = list(th), list(th)
+        tp[p] += e; tm[p] -= e
+        fd = (orc.fitc_fit(mk(tp), X, Xu, y, -1.0, mode=mode)["mll"] - orc.fitc_fit(mk(tm), X, Xu, y, -1.0, mode=mode)["mll"]) / (2 * e)
+        assert abs(fd - g[p]) < 1e-4 * (1 + abs(fd)), (mode, p, fd, g[p])
+    fdn = (orc.fitc_fit(mk(th), X, Xu, y, -1.0 + e, mode=mode)["mll"] - orc.fitc_fit(mk(th), X, Xu, y, -1.0 - e, mode=mode)["mll"]) / (2 * e)
+    assert abs(fdn - f["dmll_noise"]) < 1e-4 * (1 + abs(fdn))
