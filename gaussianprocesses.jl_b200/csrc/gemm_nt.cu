@@ -19,6 +19,7 @@
 #include "gemm_nt.cuh"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -41,6 +42,7 @@ struct GemmKP {
     int flags, zstep, m_lim, n_lim, k_lim;
     int a_has_sub, b_has_sub;
     int klo_off, bm_mod, bm_rem, bn_mod, bn_rem;
+    int gm_tri, k_down;          // rasterisation of triangular (GEMM_KLO_M) launches: group height, descending k
     int n_peer;                  // extra copies of C stored into peer GPUs' buffers (NVLink P2P), same ldc/offsets
     double* Cpeer[7];
     double alpha, beta;
@@ -66,7 +68,7 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
         // Launches whose k range starts at the tile row (GEMM_KLO_M: triangular operand) have row-dependent
         // lengths; they walk k downwards (every tile starts at the common upper end) in narrower groups so
         // that neighbours stay within the L2 reuse window.
-        const int GROUP_M = (p.flags & GEMM_KLO_M) ? 4 : 16;
+        const int GROUP_M = (p.flags & GEMM_KLO_M) ? p.gm_tri : 16;
         const int tm = p.M / BM, tn = p.N / BN;
         int rem = blockIdx.x;
         if (!(p.flags & GEMM_LOWER_ONLY)) {
@@ -242,7 +244,7 @@ gpb200_dgemm_nt_tma(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const int ar = p.a_row0 + t.zoff + t.bm * BM;
             const int br = p.b_row0 + t.zoff + t.bn * BN;
             int stage = 0; uint32_t phase = 0;
-            const bool down = (p.flags & GEMM_KLO_M) != 0;
+            const bool down = (p.flags & GEMM_KLO_M) != 0 && p.k_down;
             for (int it = t.kt_lo; it < t.kt_hi; ++it) {
                 const int kt = down ? (t.kt_hi - 1 - (it - t.kt_lo)) : it;
                 mbar_wait(&empty[stage], phase ^ 1);
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(SIMPLE_THREADS, 1) gpb200_dgemm_nt_simple(cons
     };
 
     if (t.kt_lo < t.kt_hi) {
-        const bool down = (p.flags & GEMM_KLO_M) != 0;
+        const bool down = (p.flags & GEMM_KLO_M) != 0 && p.k_down;
         auto kmap = [&](int it) { return down ? (t.kt_hi - 1 - (it - t.kt_lo)) : it; };
         gload(kmap(t.kt_lo));
         sstore(0);
@@ -411,6 +413,12 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     p.flags = d.flags; p.zstep = d.zstep; p.m_lim = d.m_lim; p.n_lim = d.n_lim; p.k_lim = d.k_lim;
     p.a_has_sub = d.A.sub.base != nullptr; p.b_has_sub = d.B.sub.base != nullptr;
     p.klo_off = d.klo_off; p.bm_mod = d.bm_mod; p.bm_rem = d.bm_rem; p.bn_mod = d.bn_mod; p.bn_rem = d.bn_rem;
+    {
+        static int gm = -1, kd = -1;                 // tuning hooks (read once): GPB200_GM_TRI, GPB200_K_DOWN
+        if (gm < 0) { const char* e = getenv("GPB200_GM_TRI"); gm = e ? atoi(e) : 4; if (gm < 1 || gm > 64) gm = 4;
+                      const char* f = getenv("GPB200_K_DOWN"); kd = f ? (atoi(f) != 0) : 1; }
+        p.gm_tri = gm; p.k_down = kd;
+    }
     p.n_peer = d.n_peer;
     for (int q = 0; q < 7; ++q) p.Cpeer[q] = q < d.n_peer ? d.Cpeer[q] : nullptr;
     p.alpha = d.alpha; p.beta = d.beta;
