@@ -33,7 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "gaussianprocesses.jl_b200"))
 
 N_FULL, D = 32768, 8
 LL, LSIG, LNOISE = 0.3, 0.3, 0.3
-N_CPU_SAMPLE = 8192
+N_CPU_SAMPLE = int(os.environ.get("GPB200_CPU_SAMPLE_N", "8192"))      # bounded CPU sample (test hook: smaller N)
 METRIC = "log-mll+grad GFLOP/s, GPE SEIso N=32768 d=8 FP64 (update_mll_and_dmll!)"
 
 
@@ -44,6 +44,25 @@ def falg(n):
 def synth(n, d, seed=1):
     rng = np.random.default_rng(seed)
     return rng.standard_normal((n, d)), rng.standard_normal(n)
+
+
+class StdoutToStderr:
+    """NCCL prints its version banner on the process's C stdout when the first communicator is created; route fd 1 to
+    stderr for that stretch so that rank 0's stdout carries nothing but the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            sys.stdout.flush()
+        finally:
+            os.dup2(self._saved, 1)
+            os.close(self._saved)
+        return False
 
 
 class ClockSampler:
@@ -160,7 +179,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
 
     N = args.n
     X, y = synth(N, D, seed=1)
@@ -174,7 +195,8 @@ def main():
     if world > 1:
         # strong scaling: the SAME N=32768 problem, work partitioned over the ranks (block-column
         # Cholesky with NCCL panel broadcasts, split inverse, row-cyclic W'W + trace)
-        gp.init_distributed()
+        with StdoutToStderr():
+            gp.init_distributed()
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     theta = np.array([LL, LSIG])
