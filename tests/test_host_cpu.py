@@ -150,3 +150,31 @@ def test_cpu_baseline_port_matches_oracle():
     assert abs(r["mll"] - o["mll"]) < 1e-10 * abs(o["mll"])
     assert np.allclose(r["dmll"], o["dmll"], rtol=1e-9)
     assert np.allclose(r["alpha"], o["alpha"], rtol=1e-9, atol=1e-12)
+
+
+def test_gpe_optimize_exception_filter_and_rollback():
+    """optimize! (src/optimize.jl:19-97): the target increases; a PosDefException / ArgumentError inside the
+    objective yields Inf and rolls the parameters back instead of aborting (optimize.jl:46-61, 72-87)."""
+    X, _, _ = make_data(40, 1, 21)
+    y = np.sin(2 * X[:, 0])
+    gp = _gp(gpb200.SEIso(0.5, 0.5), gpb200.MeanZero(), -1.0, X, y)
+    gp.update_target_and_dtarget()
+    t0 = gp.target
+    calls = {"n": 0}
+    real_factorize = gp._eng.factorize
+
+    def flaky(theta, ln, extra_nugget=0.0):
+        calls["n"] += 1
+        if calls["n"] == 2:                       # second objective evaluation blows up like a failed cholesky!
+            raise gpb200.PosDefException(7)
+        return real_factorize(theta, ln, extra_nugget)
+
+    gp._eng.factorize = flaky
+    res = gp.optimize(maxiter=20)
+    assert calls["n"] > 3                          # the optimiser carried on after the failure
+    assert gp.target > t0
+    assert np.all(np.isfinite(gp.get_params()))
+    # kern=False keeps the kernel parameters fixed (test/optim.jl)
+    k0 = gp.kernel.get_params()
+    gp.optimize(kern=False, maxiter=5)
+    assert gp.kernel.get_params() == k0
