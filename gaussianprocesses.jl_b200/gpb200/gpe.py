@@ -225,11 +225,13 @@ class GPE:
 
     # ---- optimisation (src/optimize.jl:19-97) ----------------------------------------------
     def optimize(self, noise=True, domean=True, kern=True, maxiter=100, **kw):
-        """optimize!(gp): L-BFGS on -target with the reference's exception filter
-        (PosDefException / ArgumentError -> Inf, parameters rolled back, optimize.jl:46-87)."""
+        """optimize!(gp): L-BFGS on -target with the reference's exception filter (PosDefException / ArgumentError ->
+        rejected step, parameters rolled back, optimize.jl:46-87).  Optim.jl's line search backs off from the
+        reference's `Inf`; scipy's L-BFGS-B stops on it, so a large finite penalty plays that role here."""
         from scipy.optimize import minimize
 
         flags = dict(noise=noise, domean=domean, kern=kern)
+        best = {"f": None}
 
         def fg(hyp):
             prev = self.get_params(**flags)
@@ -238,10 +240,11 @@ class GPE:
                     raise ValueError("non-finite hyper-parameter")
                 self.set_params(hyp, **flags)
                 self.update_target_and_dtarget(**flags)
+                best["f"] = -self.target if best["f"] is None else min(best["f"], -self.target)
                 return -self.target, -self.dtarget
             except (np.linalg.LinAlgError, ValueError):
                 self.set_params(prev, **flags)
-                return float("inf"), np.zeros_like(hyp)
+                return 1e10 + 1e6 * abs(best["f"] or 0.0), np.zeros_like(hyp)
 
         res = minimize(fg, self.get_params(**flags), jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter), **kw)
         self.set_params(res.x, **flags)
