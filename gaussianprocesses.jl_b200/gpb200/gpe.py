@@ -59,6 +59,15 @@ class GPE:
         self.initialise_target()
         return self
 
+    def push(self, x, y):
+        """push!(gp, x, y) (src/GPE.jl:530-539): append observations and refit (the device state is rebuilt, exactly
+        like the reference rebuilds data / cK wholesale)."""
+        x = _as_dxn(x)
+        if x.shape[0] != self.dim:
+            raise ValueError("Input observations must have the same dimension as the GP")
+        y = np.atleast_1d(np.asarray(y, dtype=np.float64)).ravel()
+        return self.fit(np.concatenate([self.x, x], axis=1), np.concatenate([self.y, y]))
+
     def reload_data(self, x, y):
         """Re-upload (x, y) of unchanged shape to the device without re-evaluating the target
         (one host->device copy of the inputs; the next update_mll! uses them)."""

@@ -178,3 +178,15 @@ def test_gpe_optimize_exception_filter_and_rollback():
     k0 = gp.kernel.get_params()
     gp.optimize(kern=False, maxiter=5)
     assert gp.kernel.get_params() == k0
+
+
+def test_gpe_push_and_fit_rebuild_state():
+    """push!(gp, x, y) / fit!(gp, x, y) (src/GPE.jl:128-136, 530-539) replace the data wholesale."""
+    X, y, _ = make_data(30, 2, 5)
+    gp = _gp(gpb200.SEIso(0.1, 0.2), gpb200.MeanConst(0.0), -1.0, X[:20], y[:20])
+    gp.push(X[20:].T, y[20:])
+    assert gp.nobs == 30 and gp.alpha.size == 30
+    o = orc.fit(gp.kernel.spec(), X, y, -1.0, ("MeanConst", 0.0))
+    assert gp.mll == pytest.approx(o["mll"], rel=1e-12)
+    with pytest.raises(ValueError):
+        gp.push(np.zeros((3, 1)), [0.0])
