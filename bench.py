@@ -25,6 +25,12 @@ import subprocess
 import sys
 import time
 
+if "reference" in sys.argv[1:] or "--impl=reference" in sys.argv[1:]:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core, so set the BLAS pool size before
+    # numpy/scipy load OpenBLAS (threadpoolctl re-asserts it at run time and the line records the count used)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -33,8 +39,11 @@ sys.path.insert(0, os.path.join(ROOT, "gaussianprocesses.jl_b200"))
 
 N_FULL, D = 32768, 8
 LL, LSIG, LNOISE = 0.3, 0.3, 0.3
-N_CPU_SAMPLE = int(os.environ.get("GPB200_CPU_SAMPLE_N", "8192"))      # bounded CPU sample (test hook: smaller N)
+N_CPU_SAMPLE = int(os.environ.get("GPB200_CPU_SAMPLE_N", "8192"))      # bounded CPU sample of our arm's cpu_baseline leg
 METRIC = "log-mll+grad GFLOP/s, GPE SEIso N=32768 d=8 FP64 (update_mll_and_dmll!)"
+WORKLOAD = ("C2: GPE SEIso(0.3,0.3) logNoise 0.3 MeanConst(0), N=%d d=8 FP64: Gram + Cholesky + alpha/mll + K^-1 + "
+            "gradient trace per step")
+CPU_BUDGET_S = float(os.environ.get("GPB200_CPU_BUDGET_S", "200"))    # wall-clock budget of the whole reference arm
 
 
 def falg(n):
@@ -109,43 +118,97 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_blas_threads():
+    """All host cores for OpenBLAS, whatever OMP_NUM_THREADS says (torchrun sets it to 1).  Returns the count in use."""
+    want = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=want)
+        import scipy.linalg  # noqa: F401  (loads the OpenBLAS that LAPACK calls go to)
+        threadpoolctl.threadpool_limits(limits=want)
+        got = [p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()]
+        return max(got) if got else want
+    except Exception:
+        return want
+
+
+def extrapolate_full(seconds, n, n_full=N_FULL):
+    """Phase-wise extrapolation of one CPU evaluation from the sample size n to the metric's N: the scalar cov! /
+    dmll_kern! loops and the alpha solve are O(N^2), dpotrf and dpotrs(-I) are O(N^3) (BLAS efficiency assumed
+    unchanged).  Returns seconds at n_full."""
+    r = float(n_full) / float(n)
+    t2 = seconds["cov_loop"] + seconds["dmll_loop"] + seconds["solve_mll"]
+    t3 = seconds["dpotrf"] + seconds["potrs_identity_ger"]
+    return t2 * r ** 2 + t3 * r ** 3
+
+
+def full_size_record():
+    """One full-size (N=32768) CPU evaluation measured on a pool box and committed (profiles/): validates the extrapolation."""
+    pth = os.path.join(ROOT, "profiles", "r02_cpu_full_size.json")
+    try:
+        return json.load(open(pth))
+    except Exception:
+        return None
+
+
 def cpu_baseline_run(n, steps=1):
     from oracle import cpu_baseline as cb
+    cores = pin_blas_threads()
     X, y = synth(n, D, seed=1)
     best, last = None, None
     for _ in range(steps):
         r = cb.seiso_mll_and_dmll(X, y, LL, LSIG, LNOISE, 0.0)
         t = r["seconds"]["total"]
-        best = t if best is None else min(best, t)
-        last = r
-    return best, last, cb.host_threads()
+        if best is None or t < best:
+            best, last = t, r
+    return best, last, cores
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's own CPU algorithm (oracle port; Julia absent) on host cores."""
+    """Reference arm: the reference's own CPU algorithm (oracle port; Julia is absent from the image) on ALL host cores.
+    Each step is a bounded sample of the C2 workload (same kernel, d, distribution; N_sample < 32768 chosen so that
+    the warm-up plus the K timed steps fit CPU_BUDGET_S); `value` is the metric at the metric's own N=32768, obtained
+    by extrapolating every phase of the measured step with its complexity, the raw sample rate is reported beside it."""
     if rank != 0:
         return
     from oracle import cpu_baseline as cb
-    n = N_CPU_SAMPLE
+    cores = pin_blas_threads()
+    per_step = CPU_BUDGET_S / (args.steps + 1)
+    # ~8.5 s per evaluation at N=8192 on the pool's 64 host cores (round-1 records); time ~ N^3
+    n = int(8192 * (per_step / 8.5) ** (1.0 / 3.0)) // 1024 * 1024
+    n = max(2048, min(N_FULL, n))
+    if os.environ.get("GPB200_CPU_SAMPLE_N"):
+        n = int(os.environ["GPB200_CPU_SAMPLE_N"])
     X, y = synth(n, D, seed=1)
-    for _ in range(max(args.warmup, 0)):
-        cb.seiso_mll_and_dmll(X, y, LL, LSIG, LNOISE, 0.0)
-        break                               # one warm-up is enough for a CPU path (thread pools, page faults)
-    ts = []
+    if args.warmup > 0:
+        cb.seiso_mll_and_dmll(X, y, LL, LSIG, LNOISE, 0.0)      # one warm-up is enough for a CPU path (thread pools, page faults)
+    ts, phases = [], None
     for _ in range(args.steps):
-        ts.append(cb.seiso_mll_and_dmll(X, y, LL, LSIG, LNOISE, 0.0)["seconds"]["total"])
-    t = float(np.mean(ts))
-    val = falg(n) / t * 1e-9
-    cores = cb.host_threads()
+        r = cb.seiso_mll_and_dmll(X, y, LL, LSIG, LNOISE, 0.0)
+        ts.append(r["seconds"]["total"])
+        phases = r["seconds"] if phases is None else {k: phases[k] + v for k, v in r["seconds"].items()}
+    phases = {k: v / args.steps for k, v in phases.items()}
+    t_sample = float(np.mean(ts))
+    rate_sample = falg(n) / t_sample * 1e-9
+    t_full = extrapolate_full(phases, n) if n != N_FULL else t_sample
+    val = falg(N_FULL) / t_full * 1e-9
+    rec = full_size_record()
+    sample = ("each step = one full update_mll_and_dmll! with the reference's algorithm (scalar cov!/dmll_kern! loops in C, "
+              "1 thread, as the reference; dpotrf + dpotrs(-I) + dger via OpenBLAS on %d threads) at N_sample=%d of 32768, d=8: "
+              "%.2f s/step = %.1f GFLOP/s at N_sample; value = F_alg(32768) / t(32768) with t extrapolated per phase "
+              "(O(N^2): cov %.2f s, dmll %.2f s, solve %.2f s; O(N^3): dpotrf %.2f s, potrs(-I)+ger %.2f s) -> %.0f s"
+              % (cores, n, t_sample, rate_sample, phases["cov_loop"], phases["dmll_loop"], phases["solve_mll"],
+                 phases["dpotrf"], phases["potrs_identity_ger"], t_full))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": t_sample * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 sample: GPE SEIso(0.3,0.3) logNoise 0.3 MeanConst(0), d=8, N=%d of 32768 "
-                               "(CPU path needs ~5 min and 34 GB at full N)" % n},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-                         "sample": "N=%d d=8, full update_mll_and_dmll! (scalar cov!/dmll_kern! loops in C, 1 thread; "
-                                   "dpotrf + dpotrs(-I) via OpenBLAS on %d threads); GFLOP/s counts F_alg=N^3+2N^2" % (n, cores)},
+        "config": {"workload": WORKLOAD % N_FULL,
+                   "sample": "N_sample=%d per step (bounded CPU sample); value is the phase-extrapolated rate at N=32768" % n,
+                   "value_kind": "extrapolated_to_full_config" if n != N_FULL else "measured_full_config",
+                   "rate_at_sample_gflops": rate_sample, "seconds_full_config_extrapolated": t_full,
+                   "full_size_measured_once": rec},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,6 +305,9 @@ def main():
 
     # ---- e2e: host buffers in, host results out, through the public GPE API -------------------
     step_e2e()
+    check = {"mll": float(gp.mll), "dmll": [float(v) for v in gp.dmll], "alpha_l1": float(np.sum(np.abs(gp.alpha))),
+             "note": "results of one e2e step (host copies of mll, dmll=[noise,beta,ll,lsigma], sum|alpha|); identical "
+                     "inputs at every n_gpus, so the lines of a scaling run must agree to ~1e-10 relative"}
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
@@ -279,6 +345,8 @@ def main():
         roof = {"bound": "tensor", "kernel": "gpb200_dgemm_nt_tma (FP64 DMMA.8x8x4 fed by TMA)",
                 "achieved": achieved, "peak": pk["dmma_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["dmma_tflops"],
                 "traffic": traffic,
+                "traffic_source": "dram__bytes_read+write of the largest launch (W'W) in the committed ncu --set full capture "
+                                  "(profiles/gemm_traffic.json); not re-measured in this run",
                 "peak_source": "DMMA.8x8x4 issue rate measured in this run (gpb200_fp64_peak); MEASURED_PEAKS.json "
                                "carries no FP64 figure -- its HBM/bf16 numbers do not bound this kernel; DFMA rate "
                                "%.1f TFLOP/s, cuBLAS DGEMM on this pool 36.5 TFLOP/s (profiles/r01_cublas_dgemm.txt)" % pk["dfma_tflops"],
@@ -286,28 +354,60 @@ def main():
                 "kernel_share_of_step": tp["gemm_ms"] / ms_step,
                 "algorithmic_flops_per_step": alg, "executed_flops_per_step": tp["gemm_flops"]}
 
-    # predict_f timing (batched, M = 4096), reported beside the metric
+    # predict_f (batched, M = 4096 test points, mean + variance), device-timed inside the library (CUDA events)
     Xs = np.random.default_rng(2).standard_normal((4096, D))
     eng.predict(Xs)                        # warm-up: sizes the cross-Gram workspace
-    t0 = time.perf_counter()
-    eng.predict(Xs)
-    predict_ms = (time.perf_counter() - t0) * 1e3
+    pms = []
+    for _ in range(3):
+        mu_p, var_p, _ = eng.predict(Xs)
+        pms.append(eng.timings()["predict"])
+    predict_ms = float(np.median(pms))
+    check["predict_mu_l1"] = float(np.sum(np.abs(mu_p)))
+    check["predict_var_sum"] = float(np.sum(var_p))
+    hbm_peak = None
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6574.5                  # B200_PROFILING.md fallback == the pool's measured copy bandwidth
+    Npad = (N + 127) // 128 * 128
+    T = Npad // 128
+    tri_bytes = 8.0 * 128 * 128 * (T * (T + 1) // 2)            # lower tiles of the N x N matrix
+    own = 1.0 / world                                          # Gram / trace tiles are dealt over the ranks
+    roof_other = {
+        "gram_lower_kernel": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+                              "achieved": (tri_bytes * own + 8.0 * N * D) / (tmr["gram"] * 1e-3) * 1e-9,
+                              "bytes": "lower 128x128 tiles written once (%.3f GB per rank) + x read" % (tri_bytes * own * 1e-9),
+                              "ms": tmr["gram"]},
+        "trace_kernel": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+                         "achieved": (tri_bytes * own + 8.0 * N * D) / (tmr["trace"] * 1e-3) * 1e-9,
+                         "bytes": "lower tiles of K^-1 read once + x", "ms": tmr["trace"]},
+        "predict_f_M4096": {"bound": "tensor", "unit": "TFLOP/s", "peak": pk["dmma_tflops"],
+                            "achieved": (float(N) ** 2 * 4096 + 2.0 * N * 4096) / (predict_ms * 1e-3) * 1e-12,
+                            "flops": "N^2 M (TRSM) + 2 N M (mean), SURVEY 8(d); includes H2D of x*, cross-Gram, D2H of mu, var",
+                            "ms": predict_ms},
+    }
+    for v in roof_other.values():
+        v["frac"] = v["achieved"] / v["peak"]
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             tcpu, res, cores = cpu_baseline_run(N_CPU_SAMPLE, steps=1)
-            cpu = {"value": falg(N_CPU_SAMPLE) / tcpu * 1e-9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-                   "sample": "N=%d d=8 (of 32768): one full update_mll_and_dmll! with the reference's algorithm -- scalar "
-                             "cov!/dmll_kern! loops (C, 1 thread) + dpotrf + dpotrs(-I) (OpenBLAS, %d threads); %.1f s; "
-                             "phases %s" % (N_CPU_SAMPLE, cores, tcpu, {k: round(v, 2) for k, v in res["seconds"].items()})}
+            t_full = extrapolate_full(res["seconds"], N_CPU_SAMPLE)
+            cpu = {"value": falg(N_FULL) / t_full * 1e-9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+                   "rate_at_sample": falg(N_CPU_SAMPLE) / tcpu * 1e-9,
+                   "sample": "N_sample=%d d=8 (of 32768): one full update_mll_and_dmll! with the reference's algorithm -- scalar "
+                             "cov!/dmll_kern! loops (C, 1 thread, as the reference) + dpotrf + dpotrs(-I) (OpenBLAS, %d threads); "
+                             "%.1f s; phases %s; value = F_alg(32768)/t(32768), t extrapolated per phase (O(N^2) loops, "
+                             "O(N^3) LAPACK) = %.0f s"
+                             % (N_CPU_SAMPLE, cores, tcpu, {k: round(v, 2) for k, v in res["seconds"].items()}, t_full),
+                   "full_size_measured_once": full_size_record()}
         val = falg(N) / (ms_step * 1e-3) * 1e-9
         line = {
             "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: GPE SEIso(0.3,0.3) logNoise 0.3 MeanConst(0), N=%d d=8 FP64: Gram + Cholesky + "
-                                   "alpha/mll + K^-1 + gradient trace per step" % N,
+            "config": {"workload": WORKLOAD % N,
                        "l2": "working set (two 8.6 GB N x N FP64 matrices) exceeds the 126 MB L2; no flush needed",
                        "parallelism": "1 GPU" if world == 1 else
                        "%d GPUs: 1-D block-cyclic block columns (NCCL panel broadcast over NVLink, look-ahead), "
@@ -320,6 +420,8 @@ def main():
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "roofline_other": roof_other,
+            "check": check,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -202,6 +202,18 @@ int fail(gpb200_handle* h, int code, const char* msg) {
     return code;
 }
 
+// unmap every peer buffer imported by gpb200_ipc_import (a realloc or a re-import makes them stale)
+void close_peer_maps(gpb200_handle* h) {
+    for (int q = 0; q < h->n_peer; ++q) {
+        cudaIpcCloseMemHandle(h->peer_F[q]); cudaIpcCloseMemHandle(h->peer_Dinv[q]);
+        cudaIpcCloseMemHandle(h->peer_DinvT[q]); cudaIpcCloseMemHandle(h->peer_logd[q]);
+        cudaIpcCloseMemHandle(h->peer_sig[q]);
+        h->peer_F[q] = h->peer_Dinv[q] = h->peer_DinvT[q] = h->peer_logd[q] = nullptr; h->peer_sig[q] = nullptr;
+    }
+    (void)cudaGetLastError();
+    h->p2p = false; h->n_peer = 0;
+}
+
 void free_data(gpb200_handle* h) {
     double** ptrs[] = {&h->x, &h->F, &h->G, &h->Dinv, &h->DinvT, &h->logd, &h->noise_var, &h->r0, &h->r1,
                        &h->y1, &h->alpha, &h->scal, &h->part, &h->trace_out, &h->xs, &h->Kst, &h->Kss,
@@ -209,14 +221,7 @@ void free_data(gpb200_handle* h) {
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
     if (h->flags) { cudaFree(h->flags); h->flags = nullptr; }
-    if (h->p2p) {
-        for (int q = 0; q < h->n_peer; ++q) {
-            cudaIpcCloseMemHandle(h->peer_F[q]); cudaIpcCloseMemHandle(h->peer_Dinv[q]);
-            cudaIpcCloseMemHandle(h->peer_DinvT[q]); cudaIpcCloseMemHandle(h->peer_logd[q]);
-            cudaIpcCloseMemHandle(h->peer_sig[q]);
-        }
-        h->p2p = false; h->n_peer = 0;
-    }
+    close_peer_maps(h);                        // peers' mappings refer to the old buffers whether or not p2p is switched on
     if (h->sig) { cudaFree(h->sig); h->sig = nullptr; }
     if (h->peer_sig_dev) { cudaFree(h->peer_sig_dev); h->peer_sig_dev = nullptr; }
     for (int i = 0; i < 2; ++i) { if (h->pack[i]) cudaFree(h->pack[i]); h->pack[i] = nullptr; }
@@ -1444,6 +1449,7 @@ int gpb200_ipc_import(gpb200_handle* h, int nranks, const char* all) {
     if (!h || !all) return GPB200_EINVAL;
     if (nranks != h->nranks || nranks < 2 || nranks > 8) return fail(h, GPB200_EINVAL, "ipc_import: call comm_init first; 2..8 ranks");
     CK(cudaSetDevice(h->device));
+    close_peer_maps(h);                        // re-import: drop the previous mappings first
     int n = 0;
     for (int q = 0; q < nranks; ++q) {
         if (q == h->rank) continue;

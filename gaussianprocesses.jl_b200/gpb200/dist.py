@@ -20,11 +20,18 @@ def init_engine_comm(engine, p2p=True):
     uid = broadcast_bytes(engine.nccl_unique_id() if rank == 0 else None, src=0)
     engine.comm_init(world, rank, uid)
     if p2p and hasattr(engine, "ipc_export"):
-        # fused panel broadcast: map every peer's factor buffers over NVLink (CUDA IPC)
-        blobs = [None] * world
-        dist.all_gather_object(blobs, engine.ipc_export())
-        engine.ipc_import(blobs)
+        exchange_ipc(engine)
     return world, rank
+
+
+def exchange_ipc(engine):
+    """Fused panel broadcast: map every peer's factor buffers over NVLink (CUDA IPC).  Collective; must be repeated
+    after a set_data that reallocates the device buffers (the old mappings are closed by the engine)."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    blobs = [None] * world
+    dist.all_gather_object(blobs, engine.ipc_export())
+    engine.ipc_import(blobs)
 
 
 def max_over_ranks(value):

@@ -26,6 +26,10 @@ def _as_dxn(x):
     return x
 
 
+class _RejectedStep(Exception):
+    """optimize(): a trial point outside the domain (non-finite hyper-parameter)."""
+
+
 class GPE:
     def __init__(self, x, y, mean=None, kernel=None, logNoise=-2.0, device=0, engine=None):
         if kernel is None or not isinstance(kernel, Kernel):
@@ -55,6 +59,9 @@ class GPE:
         self.dim, self.nobs = x.shape
         self._xpm = np.ascontiguousarray(x.T)            # (nobs, dim): Julia's memory layout
         self._eng.set_data(self._xpm)
+        if getattr(self, "_world", 1) > 1 and getattr(self, "_p2p", False):
+            from .dist import exchange_ipc                # buffers may have been reallocated: re-map the peers
+            exchange_ipc(self._eng)
         self._sync_kernel()
         self.initialise_target()
         return self
@@ -92,6 +99,7 @@ class GPE:
             env = os.environ.get("GPB200_P2P")
             p2p = (env != "0") if env is not None else (tdist.is_initialized() and tdist.get_world_size() <= 4)
         world, rank = init_engine_comm(self._eng, p2p=p2p)
+        self._world, self._p2p = world, bool(p2p)
         if world > 1:
             self.update_target()
         return world, rank
@@ -123,8 +131,10 @@ class GPE:
 
     def update_dmll(self, noise=True, domean=True, kern=True):
         """update_dmll!(gp, precomp) (src/GPE.jl:298-324)."""
-        self._eng.grad_prepare()                                  # precompute! -> get_ααinvcKI!
-        gk_full, trA = self._eng.grad_kernel()                    # dmll_kern! + tr(A)
+        gk_full, trA = None, None
+        if noise or kern:                                         # mean-only gradient needs neither K^-1 nor the trace
+            self._eng.grad_prepare()                              # precompute! -> get_ααinvcKI!
+            gk_full, trA = self._eng.grad_kernel()                # dmll_kern! + tr(A)
         out = []
         if noise:
             if np.ndim(self.logNoise):
@@ -246,14 +256,17 @@ class GPE:
             prev = self.get_params(**flags)
             try:
                 if not np.all(np.isfinite(hyp)):
-                    raise ValueError("non-finite hyper-parameter")
+                    raise _RejectedStep("non-finite hyper-parameter")
                 self.set_params(hyp, **flags)
                 self.update_target_and_dtarget(**flags)
                 best["f"] = -self.target if best["f"] is None else min(best["f"], -self.target)
                 return -self.target, -self.dtarget
-            except (np.linalg.LinAlgError, ValueError):
+            except (np.linalg.LinAlgError, _RejectedStep):            # PosDefException subclasses LinAlgError
+                # only the reference's filtered exceptions (PosDefException / non-finite parameters, optimize.jl:46-87)
+                # reject a step; call-order / shape errors (ValueError from the engine) propagate.  The penalty's
+                # gradient points back to the last accepted point so that the line search retreats.
                 self.set_params(prev, **flags)
-                return 1e10 + 1e6 * abs(best["f"] or 0.0), np.zeros_like(hyp)
+                return 1e10 + 1e6 * abs(best["f"] or 0.0), np.asarray(hyp, dtype=np.float64) - prev
 
         res = minimize(fg, self.get_params(**flags), jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter), **kw)
         self.set_params(res.x, **flags)

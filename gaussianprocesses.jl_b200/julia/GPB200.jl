@@ -41,19 +41,27 @@ mutable struct B200PDMat <: AbstractPDMat{Float64}
     n::Int
     exposed::Vector{Int}          # positions of get_params(kernel) inside the device's full theta
     ntheta::Int                   # length of the device's full parameter vector (FixedKernel may hide some)
+    xid::UInt                     # objectid of the x last uploaded (skip the H2D copy while it is unchanged)
+    xsize::Tuple{Int,Int}
+    ops::Vector{Int32}            # kernel program last sent (skip gpb200_set_kernel while the tree shape is unchanged)
+    dims::Vector{Int32}
     function B200PDMat(device::Int, n::Int)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:gpb200_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
         rc == 0 || error("gpb200_create: ", unsafe_string(ccall((:gpb200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
-        obj = new(h[], n, Int[], 0)
+        obj = new(h[], n, Int[], 0, UInt(0), (0, 0), Int32[], Int32[])
         finalizer(o -> ccall((:gpb200_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle), obj)
         return obj
     end
 end
 
-struct B200Precompute <: AbstractGradientPrecompute
-    cK::B200PDMat
+# precompute!(pre, gp) runs the inverse AND the fused trace once; dmll_kern! / dmll_noise read the cached result
+mutable struct B200Precompute <: AbstractGradientPrecompute
+    g::Vector{Float64}            # full kernel gradient (device parameter order)
+    trA::Float64                  # tr(alpha alpha' - K_y^-1)
+    exposed::Vector{Int}
 end
+B200Precompute() = B200Precompute(Float64[], NaN, Int[])
 
 # error convention of include/gpb200.h -> the exceptions optimize!/mcmc filter (src/optimize.jl:46-87)
 function check(cK::B200PDMat, rc::Integer, what)
@@ -101,19 +109,31 @@ size(a::B200PDMat) = (a.n, a.n)
 size(a::B200PDMat, i::Int) = a.n
 dim(a::B200PDMat) = a.n
 
-function update_cK!(cK::B200PDMat, x::AbstractMatrix, kernel::Kernel, logNoise, data::KernelData, ::B200Covariance)
-    X = Matrix{Float64}(x)                       # Adjoint / SubArray / ElasticArray -> dense d x N (gotcha 1)
-    d, n = size(X)
-    check(cK, ccall((:gpb200_set_data, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64), cK.handle, n, d, X, d), "set_data")
+# update_cK! (src/GPE.jl:169-186).  Two methods, typed like the reference's pair (logNoise::Real / ::AbstractVector)
+# so that they are strictly more specific than update_cK!(::AbstractPDMat, ..., ::CovarianceStrategy).
+function b200_update!(cK::B200PDMat, x::AbstractMatrix, kernel::Kernel, ln::Vector{Float64})
+    d, n = size(x)
+    if objectid(x) != cK.xid || (d, n) != cK.xsize       # fit!/push!/append! replace or grow x; optimiser steps do not
+        X = Matrix{Float64}(x)                   # Adjoint / SubArray / ElasticArray -> dense d x N (gotcha 1)
+        check(cK, ccall((:gpb200_set_data, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64), cK.handle, n, d, X, d), "set_data")
+        cK.xid = objectid(x); cK.xsize = (d, n); cK.n = n
+        empty!(cK.ops)
+    end
     ops, dims, theta, exposed = flatten(kernel, d)
+    if ops != cK.ops || dims != cK.dims
+        check(cK, ccall((:gpb200_set_kernel, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32),
+                        cK.handle, length(ops) ÷ 6, ops, length(dims), dims, length(theta)), "set_kernel")
+        cK.ops = ops; cK.dims = dims
+    end
     cK.exposed = exposed; cK.ntheta = length(theta)
-    check(cK, ccall((:gpb200_set_kernel, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Int32),
-                    cK.handle, length(ops) ÷ 6, ops, length(dims), dims, length(theta)), "set_kernel")
-    ln = Float64.(vcat(logNoise))                # Scalar or VectorParam (src/GPE.jl:169 vs :177)
     check(cK, ccall((:gpb200_factorize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64),
                     cK.handle, theta, ln, length(ln), 0.0), "factorize")          # rc > 0 -> PosDefException
     return cK
 end
+update_cK!(cK::B200PDMat, x::AbstractMatrix, kernel::Kernel, logNoise::Real, data::KernelData, ::B200Covariance) =
+    b200_update!(cK, x, kernel, Float64[logNoise])
+update_cK!(cK::B200PDMat, x::AbstractMatrix, kernel::Kernel, logNoise::AbstractVector, data::KernelData, ::B200Covariance) =
+    b200_update!(cK, x, kernel, Vector{Float64}(logNoise))
 
 function \(cK::B200PDMat, y::AbstractVector)                                      # src/GPE.jl:208
     out = Vector{Float64}(undef, cK.n)
@@ -134,30 +154,25 @@ function Matrix(cK::B200PDMat)                                                  
 end
 tr(cK::B200PDMat) = tr(Matrix(cK))
 
-init_precompute(::B200Covariance, X, y, k) = nothing                              # replaced per-gp below
-init_precompute(gp::GPE{X,Y,M,K,CS,D,P}) where {X,Y,M,K,CS<:B200Covariance,D,P} = B200Precompute(gp.cK)
+init_precompute(::B200Covariance, X, y, k) = B200Precompute()                      # src/GPE.jl:256-260: no N x N host buffer
 
 function precompute!(pre::B200Precompute, gp)                                     # src/GPE.jl:262-264
-    check(pre.cK, ccall((:gpb200_grad_prepare, LIB), Cint, (Ptr{Cvoid},), pre.cK.handle), "grad_prepare")
-end
-
-function grad_full(pre::B200Precompute, gp)
-    g = Vector{Float64}(undef, max(pre.cK.ntheta, 1)); trA = Ref{Float64}(0.0)
-    check(pre.cK, ccall((:gpb200_grad_kernel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
-                        pre.cK.handle, gp.alpha, g, trA), "grad_kernel")
-    return g, trA[]
+    cK = gp.cK
+    check(cK, ccall((:gpb200_grad_prepare, LIB), Cint, (Ptr{Cvoid},), cK.handle), "grad_prepare")
+    g = Vector{Float64}(undef, max(cK.ntheta, 1)); trA = Ref{Float64}(0.0)
+    check(cK, ccall((:gpb200_grad_kernel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                    cK.handle, gp.alpha, g, trA), "grad_kernel")                   # one fused pass: P gradients + tr(A)
+    pre.g = g; pre.trA = trA[]; pre.exposed = cK.exposed
+    return pre
 end
 
 function dmll_kern!(dmll::AbstractVector, gp, pre::B200Precompute, ::B200Covariance)   # src/GPE.jl:265-267
-    g, _ = grad_full(pre, gp)
-    dmll .= g[pre.cK.exposed]                     # FixedKernel selection (fixed_kernel.jl:64-66)
+    dmll .= pre.g[pre.exposed]                    # FixedKernel selection (fixed_kernel.jl:64-66)
     return dmll
 end
 
-function dmll_noise(gp::GPE, pre::B200Precompute, ::B200Covariance)               # src/GPE.jl:273-281
-    _, trA = grad_full(pre, gp)
-    return exp(2 * GaussianProcesses.get_value(gp.logNoise)) * trA
-end
+dmll_noise(gp::GPE, pre::B200Precompute, ::B200Covariance) =                      # src/GPE.jl:273-281
+    exp(2 * GaussianProcesses.get_value(gp.logNoise)) * pre.trA
 
 # leave-one-out predictions (src/crossvalidation.jl:8-13) without materialising inv(Σ) on the host
 function GaussianProcesses.predict_LOO(cK::B200PDMat, alpha::AbstractVector{<:Real}, y::AbstractVector{<:Real})
@@ -169,27 +184,31 @@ function GaussianProcesses.predict_LOO(cK::B200PDMat, alpha::AbstractVector{<:Re
 end
 
 # batched prediction instead of the per-column loop of src/GP.jl:72-76
-function predict_raw(gp::GPE, x::AbstractMatrix, full_cov::Bool)
-    size(x, 1) == gp.dim || throw(ArgumentError("Gaussian Process object and input observations do not have consistent dimensions"))
+function predict_raw(cK::B200PDMat, x::AbstractMatrix, alpha::AbstractVector, full_cov::Bool)
     X = Matrix{Float64}(x); M = size(X, 2)
     mu = Vector{Float64}(undef, M)
-    var = full_cov ? C_NULL : Vector{Float64}(undef, M)
-    cov = full_cov ? Matrix{Float64}(undef, M, M) : C_NULL
-    check(gp.cK, ccall((:gpb200_predict, LIB), Cint,
-                       (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                       gp.cK.handle, M, X, size(X, 1), gp.alpha, mu, var, cov), "predict")
-    mu .+= mean(gp.mean, X)
+    var = full_cov ? Float64[] : Vector{Float64}(undef, M)
+    cov = full_cov ? Matrix{Float64}(undef, M, M) : Matrix{Float64}(undef, 0, 0)
+    check(cK, ccall((:gpb200_predict, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    cK.handle, M, X, size(X, 1), Vector{Float64}(alpha), mu,
+                    full_cov ? Ptr{Float64}(C_NULL) : pointer(var), full_cov ? pointer(cov) : Ptr{Float64}(C_NULL)), "predict")
     return mu, (full_cov ? cov : var)
 end
 
 function predict_f(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractMatrix; full_cov::Bool=false) where {X,Y,M,K,CS<:B200Covariance,D,P}
-    mu, s = predict_raw(gp, x, full_cov)
-    return full_cov ? (mu, s) : (mu, max.(s, 0.0))                                 # src/GP.jl:75
+    size(x, 1) == gp.dim || throw(ArgumentError("Gaussian Process object and input observations do not have consistent dimensions"))
+    full_cov && return predict_full(gp, x)                                         # -> predictMVN below (src/GPE.jl:399)
+    mu, s = predict_raw(gp.cK, x, gp.alpha, false)
+    return mu .+ mean(gp.mean, Matrix{Float64}(x)), max.(s, 0.0)                   # src/GP.jl:75
 end
 
-function predictMVN(xpred::AbstractMatrix, xtrain, ytrain, kernel::Kernel, meanf::Mean, alpha,
-                    ::B200Covariance, Ktrain::B200PDMat)                           # src/GP.jl:39-49
-    error("predictMVN(B200Covariance) is reached through predict_f(gp, x); call that instead")
+# predictMVN (src/GP.jl:39-49): mean + FULL predictive covariance through gpb200_predict(cov != NULL); this is what
+# predict_full / predict_f(full_cov=true) / rand(gp, X) reach.
+function predictMVN(xpred::AbstractMatrix, xtrain::AbstractMatrix, ytrain::AbstractVector, kernel::Kernel, meanf::Mean,
+                    alpha::AbstractVector, ::B200Covariance, Ktrain::B200PDMat)
+    mu, Sigma_raw = predict_raw(Ktrain, xpred, alpha, true)
+    return mu .+ mean(meanf, Matrix{Float64}(xpred)), Sigma_raw
 end
 
 # =====================================================================================================
@@ -210,6 +229,7 @@ mutable struct B200SparsePDMat <: AbstractPDMat{Float64}
     handle::Ptr{Cvoid}
     n::Int
     exposed::Vector{Int}
+    ntheta::Int
     alpha::Vector{Float64}     # Sigma^-1 r of the last `\`
     logdet::Float64
     function B200SparsePDMat(cs::B200Sparse, n::Int)

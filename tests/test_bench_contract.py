@@ -28,6 +28,26 @@ def test_reference_arm_prints_contract_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["gpu_launches"] == 0
     assert j["value"] > 0 and "workload" in j["config"]
+    # same config string as our arm; the value is the phase-extrapolated full-config rate, the raw sample rate sits beside it
+    assert "N=32768" in j["config"]["workload"] and j["config"]["value_kind"] == "extrapolated_to_full_config"
+    assert j["config"]["rate_at_sample_gflops"] > 0 and "N_sample=768" in j["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_ignores_torchrun_thread_pinning():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core and say how many."""
+    env = dict(os.environ, GPB200_CPU_SAMPLE_N="512", OMP_NUM_THREADS="1", RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert j["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+
+
+def test_phase_extrapolation_model():
+    import bench
+    sec = {"cov_loop": 1.0, "dmll_loop": 2.0, "solve_mll": 0.5, "dpotrf": 3.0, "potrs_identity_ger": 10.0}
+    assert abs(bench.extrapolate_full(sec, 8192, 32768) - (3.5 * 16 + 13.0 * 64)) < 1e-9
+    assert abs(bench.extrapolate_full(sec, 32768, 32768) - 16.5) < 1e-9
 
 
 def test_reference_arm_other_ranks_stay_silent():

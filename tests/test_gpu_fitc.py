@@ -1,12 +1,21 @@
 """GPU: the FITC sparse strategy (src/sparse/fully_indep_train_conditional.jl) through the C ABI against
-the CPU oracle.  Tolerances: the 1e-10 nuggets on K_uu / Sigma_QR are part of the reference's arithmetic
-and amplify rounding by cond(K_uu) (~1e5 here), hence 1e-9 on mll and 1e-7 on alpha / predictions."""
+the CPU oracle.  Tolerance: the north-star's 1e-10 where K_uu is well conditioned (test_fitc_well_conditioned...);
+with randomly drawn inducing points K_uu + 1e-10 I (the reference's own nugget, fitc.jl:139-141) has
+cond ~ 1e5..1e9 and ANY two factorisation orders differ by ~cond(K_uu) eps, so there the bound asserted is
+max(1e-10, C cond(K_uu) eps), with cond measured in the test and printed next to the observed errors."""
 import numpy as np
 import pytest
 
 from oracle import gp_oracle as orc
 
 pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps
+
+
+def _cond_kuu(spec, Xu):
+    w = np.linalg.eigvalsh(orc.cov(spec, Xu) + 1e-10 * np.eye(Xu.shape[0]))
+    return float(w[-1] / w[0])
 
 
 def _rel(a, b):
@@ -25,9 +34,14 @@ def test_fitc_matches_oracle(N, M, d, kname):
     gp = g.FITC(X.T, Xu.T, y, g.MeanConst(0.1), k, -1.0)
     gp.update_dmll_noise_mean()
     o = orc.fitc_fit(k.spec(), X, Xu, y, -1.0, ("MeanConst", 0.1))
-    assert abs(gp.mll - o["mll"]) <= 1e-9 * abs(o["mll"])
-    assert abs(gp.logdet - o["logdet"]) <= 1e-9 * abs(o["logdet"]) + 1e-9
-    assert _rel(gp.alpha, o["alpha"]) < 1e-7
+    cond = _cond_kuu(k.spec(), Xu)
+    tol_s = max(1e-10, 4.0 * cond * EPS)              # scalars (mll, logdet): errors average out over M pivots
+    tol_v = max(1e-10, 64.0 * cond * EPS)             # vectors (alpha, predictions): worst entry
+    e_mll, e_ld, e_al = abs(gp.mll - o["mll"]) / abs(o["mll"]), abs(gp.logdet - o["logdet"]) / abs(o["logdet"]), _rel(gp.alpha, o["alpha"])
+    print("FITC %s N=%d M=%d: cond(K_uu+1e-10I)=%.2e  mll %.2e logdet %.2e alpha %.2e  (bounds %.1e / %.1e)"
+          % (kname, N, M, cond, e_mll, e_ld, e_al, tol_s, tol_v))
+    assert e_mll <= min(tol_s, 1e-9) and e_ld <= min(tol_s, 1e-9) + 1e-12
+    assert e_al <= min(tol_v, 1e-7)
     assert abs(gp.dmll[0] - o["dmll_noise"]) <= 1e-6 * abs(o["dmll_noise"]) + 1e-8
     assert abs(gp.dmll[1] - o["dmll_mean"][0]) <= 1e-6 * abs(o["dmll_mean"][0]) + 1e-8
     mu, s2 = gp.predict_f(Xs.T)
@@ -103,3 +117,29 @@ def test_sor_dtc_match_oracle(mode):
     mo, vo = orc.fitc_predict(k.spec(), X, Xu, o, Xs)
     assert _rel(mu, mo) < 1e-7
     assert np.max(np.abs(s2 - vo)) <= 1e-7 * np.max(np.abs(vo)) + 1e-9
+
+
+def test_fitc_well_conditioned_inducing_set_meets_1e10():
+    """Inducing points on a coarse grid (cond(K_uu) ~ 10): the north-star tolerance 1e-10 holds for mll, logdet,
+    alpha and the predictions -- the looser bounds above are conditioning, not the engine."""
+    import gpb200 as g
+    rng = np.random.default_rng(21)
+    N, d = 4000, 2
+    X = rng.uniform(-3, 3, (N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    gx = np.linspace(-3, 3, 7)
+    Xu = np.array([[a, b] for a in gx for b in gx])
+    Xs = rng.uniform(-3, 3, (64, d))
+    k = g.SEIso(-0.7, 0.1)
+    cond = _cond_kuu(k.spec(), Xu)
+    assert cond < 1e3
+    gp = g.FITC(X.T, Xu.T, y, g.MeanConst(0.1), k, -1.0)
+    gp.update_dmll()
+    o = orc.fitc_fit(k.spec(), X, Xu, y, -1.0, ("MeanConst", 0.1))
+    errs = (abs(gp.mll - o["mll"]) / abs(o["mll"]), abs(gp.logdet - o["logdet"]) / abs(o["logdet"]), _rel(gp.alpha, o["alpha"]))
+    print("FITC grid inducing set: cond %.1f, mll %.2e logdet %.2e alpha %.2e" % ((cond,) + errs))
+    assert max(errs) <= 1e-10
+    mu, s2 = gp.predict_f(Xs.T)
+    mo, vo = orc.fitc_predict(k.spec(), X, Xu, o, Xs, ("MeanConst", 0.1))
+    assert _rel(mu, mo) <= 1e-10 and np.max(np.abs(s2 - vo)) <= 1e-10 * np.max(np.abs(vo)) + 1e-13
+    gk = orc.fitc_dmll_kern(k.spec(), X, Xu, o)
+    assert np.allclose(gp.dmll[2:], gk, rtol=1e-8, atol=1e-9)

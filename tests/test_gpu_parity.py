@@ -193,6 +193,25 @@ def test_gpe_mirror_end_to_end(engine):
         fd[i] /= 2e-5
     gp.set_params(p0); gp.update_target_and_dtarget()
     assert np.allclose(gp.dtarget, fd, rtol=1e-4, atol=1e-4)
+    # LOO predictions (test/test_crossvalidation.jl: analytic LOO == refit without point i).  Checked on the initial,
+    # well-conditioned hyper-parameters (cond(K_y) ~ 1e4): after optimize() on noiseless data cond(K_y) ~ 1e12 and no two
+    # inverses agree to 1e-8.  diag(K_y^-1) is verified by a residual (K_y z_i = e_i  =>  [K^-1]_ii = z_i[i]) rather than
+    # against a second explicit inverse.
+    mu_loo, s2_loo = gp.predict_LOO()
+    Ky = orc.gram(gp.kernel.spec(), X, gp.logNoise)
+    r = y - gp.mean.mean(X)
+    idx = np.array([0, 17, 63, 128, 199])
+    Z = np.linalg.solve(Ky, np.eye(200)[:, idx])
+    assert np.max(np.abs(Ky @ Z - np.eye(200)[:, idx])) < 1e-10
+    assert np.allclose(1.0 / s2_loo[idx], Z[idx, np.arange(idx.size)], rtol=1e-9)
+    Kinv = np.linalg.inv(Ky)
+    assert np.allclose(s2_loo, 1.0 / np.diag(Kinv), rtol=1e-8)
+    assert np.allclose(mu_loo, y - (Kinv @ r) / np.diag(Kinv), rtol=1e-7, atol=1e-9)
+    keep = np.arange(200) != 17
+    f17 = orc.fit(gp.kernel.spec(), X[keep], y[keep], gp.logNoise, gp.mean.spec())
+    m17, v17 = orc.predict_f(gp.kernel.spec(), X[keep], f17, X[17:18], gp.mean.spec())
+    assert abs(mu_loo[17] - m17[0]) < 1e-7 and abs(s2_loo[17] - (v17[0] + gp.noise_variance())) < 1e-7
+    assert np.isfinite(gp.logp_LOO())
     t0 = gp.target
     gp.optimize(maxiter=15)
     assert gp.target > t0
@@ -204,18 +223,8 @@ def test_gpe_mirror_end_to_end(engine):
         gp.predict_f(np.zeros((3, 5)))
     my, sy = gp.predict_y(X.T[:, :5])
     assert np.allclose(sy, s2[:5] + gp.noise_variance())
-    # LOO predictions (test/test_crossvalidation.jl: analytic LOO == refit without point i)
-    mu_loo, s2_loo = gp.predict_LOO()
-    Kinv = np.linalg.inv(orc.gram(gp.kernel.spec(), X, gp.logNoise))
-    r = y - gp.mean.mean(X)
-    assert np.allclose(s2_loo, 1.0 / np.diag(Kinv), rtol=1e-8)
-    assert np.allclose(mu_loo, y - (Kinv @ r) / np.diag(Kinv), rtol=1e-7, atol=1e-9)
-    keep = np.arange(200) != 17
-    f17 = orc.fit(gp.kernel.spec(), X[keep], y[keep], gp.logNoise, gp.mean.spec())
-    m17, v17 = orc.predict_f(gp.kernel.spec(), X[keep], f17, X[17:18], gp.mean.spec())
-    assert abs(mu_loo[17] - m17[0]) < 1e-7 and abs(s2_loo[17] - (v17[0] + gp.noise_variance())) < 1e-7
-    assert np.isfinite(gp.logp_LOO())
     # rand(gp, X, n) (test/gp.jl: posterior samples): right shape, sample mean -> predictive mean
+    gp.set_params(p0); gp.update_target()            # back to the well-conditioned initial hyper-parameters
     Xq = X.T[:, :6] + 0.05
     draws = gp.rand(Xq, 4000, rng=np.random.default_rng(0))
     mq, cq = gp.predict_f(Xq, full_cov=True)
