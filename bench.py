@@ -126,7 +126,7 @@ def pin_blas_threads():
         threadpoolctl.threadpool_limits(limits=want)
         import scipy.linalg  # noqa: F401  (loads the OpenBLAS that LAPACK calls go to)
         threadpoolctl.threadpool_limits(limits=want)
-        got = [p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()]
+        got = [p.get("num_threads", 1) for p in threadpoolctl.threadpool_info() if p.get("user_api") == "blas"]
         return max(got) if got else want
     except Exception:
         return want

@@ -42,6 +42,7 @@ struct GemmKP {
     int flags, zstep, m_lim, n_lim, k_lim;
     int a_has_sub, b_has_sub;
     int klo_off, bm_mod, bm_rem, bn_mod, bn_rem;
+    int bm_div, bm_off, bn_div, bn_off;
     int gm_tri, k_down;          // rasterisation of triangular (GEMM_KLO_M) launches: group height, descending k
     int n_peer;                  // extra copies of C stored into peer GPUs' buffers (NVLink P2P), same ldc/offsets
     double* Cpeer[7];
@@ -105,9 +106,11 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
         }
     }
     t.valid = (t.bm * BM < Mz) && (t.bn * BN < Nz) && (!(p.flags & GEMM_LOWER_ONLY) || t.bn <= t.bm) &&
-              (!(p.flags & GEMM_SKIP_FIRST) || t.bm != 0 || t.bn != 0) && (p.bm_mod <= 1 || (t.bm % p.bm_mod) == p.bm_rem) &&
-              (p.bn_mod <= 1 || (t.bn % p.bn_mod) == p.bn_rem);
+              (!(p.flags & GEMM_SKIP_FIRST) || t.bm != 0 || t.bn != 0) &&
+              (p.bm_mod <= 1 || (((t.bm + p.bm_off) / p.bm_div) % p.bm_mod) == p.bm_rem) &&
+              (p.bn_mod <= 1 || (((t.bn + p.bn_off) / p.bn_div) % p.bn_mod) == p.bn_rem);
     t.kt_lo = (p.flags & GEMM_KLO_M) ? (p.klo_off + t.bm * BM) / BK : 0;
+    if (p.flags & GEMM_KLO_N) t.kt_lo = max(t.kt_lo, t.bn * (BN / BK));
     int hi = Kz > 0 ? Kz / BK : 0;
     if (p.flags & GEMM_KHI_M) hi = min(hi, (t.bm + 1) * (BM / BK));
     if (p.flags & GEMM_KHI_N) hi = min(hi, (t.bn + 1) * (BN / BK));
@@ -413,6 +416,7 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     p.flags = d.flags; p.zstep = d.zstep; p.m_lim = d.m_lim; p.n_lim = d.n_lim; p.k_lim = d.k_lim;
     p.a_has_sub = d.A.sub.base != nullptr; p.b_has_sub = d.B.sub.base != nullptr;
     p.klo_off = d.klo_off; p.bm_mod = d.bm_mod; p.bm_rem = d.bm_rem; p.bn_mod = d.bn_mod; p.bn_rem = d.bn_rem;
+    p.bm_div = d.bm_div > 0 ? d.bm_div : 1; p.bm_off = d.bm_off; p.bn_div = d.bn_div > 0 ? d.bn_div : 1; p.bn_off = d.bn_off;
     {
         static int gm = -1, kd = -1;                 // tuning hooks (read once): GPB200_GM_TRI, GPB200_K_DOWN
         if (gm < 0) { const char* e = getenv("GPB200_GM_TRI"); gm = e ? atoi(e) : 4; if (gm < 1 || gm > 64) gm = 4;

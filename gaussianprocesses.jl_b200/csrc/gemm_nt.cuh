@@ -13,6 +13,7 @@ enum : int {
     GEMM_KHI_M      = 4,   // k ends at (bm+1)*128      (A rows are lower-triangular)
     GEMM_KHI_N      = 8,   // k ends at (bn+1)*128      (B rows are lower-triangular)
     GEMM_SKIP_FIRST = 16,  // tile (0,0) is computed elsewhere (look-ahead of the next diagonal tile)
+    GEMM_KLO_N      = 32,  // k starts at bn*128        (B rows are upper-triangular in the frame)
 };
 
 // A matrix living in a handle-owned buffer.  `map` is the TMA descriptor of the whole buffer
@@ -40,8 +41,10 @@ struct GemmDesc {
     int zstep;          // added to every row0/col0 per batch index (diagonal stepping)
     int m_lim, n_lim, k_lim;   // per-batch clipping: M_z = min(M, m_lim - z*zstep) etc. (<=0: skip)
     int klo_off;        // GEMM_KLO_M: k starts at klo_off + bm*128 (row slice of a triangular operand)
-    int bm_mod, bm_rem; // multi-GPU work split: only tile rows with bm % bm_mod == bm_rem (bm_mod <= 1: all)
+    int bm_mod, bm_rem; // multi-GPU work split: only tile rows with ((bm + bm_off) / bm_div) % bm_mod == bm_rem (bm_mod <= 1: all)
     int bn_mod, bn_rem; // same for tile columns
+    int bm_div, bm_off; // block-cyclic ownership: bm_div tiles per block (0/1: tile-cyclic), bm_off = global tile index of tile row 0
+    int bn_div, bn_off;
     int n_peer;         // fused broadcast: C is additionally stored to these peer-mapped buffers (not with LOWER_ONLY)
     double* Cpeer[7];
 };

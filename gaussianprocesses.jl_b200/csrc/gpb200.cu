@@ -41,6 +41,7 @@
 #include "gram.cuh"
 #include "kprog.cuh"
 #include "potrf_base.cuh"
+#include "shard_kernels.cuh"
 #include "vec.cuh"
 
 namespace {
@@ -48,6 +49,14 @@ constexpr int TILE = 128;
 constexpr double LOG2PI = 1.8378770664093453;
 std::string g_create_error;
 }  // namespace
+
+// a virtual address range backed by physical memory only where `runs` say so (CUDA VMM: cuMemAddressReserve / cuMemMap)
+struct VmBuf {
+    CUdeviceptr base = 0;
+    size_t va_size = 0;
+    std::vector<std::pair<size_t, size_t>> runs;          // (offset, bytes) of every mapped run
+    std::vector<CUmemGenericAllocationHandle> handles;    // one physical allocation per run
+};
 
 struct gpb200_handle {
     int device = 0;
@@ -62,6 +71,7 @@ struct gpb200_handle {
     double *F = nullptr, *G = nullptr, *Dinv = nullptr, *DinvT = nullptr, *logd = nullptr;
     double *noise_var = nullptr, *r0 = nullptr, *r1 = nullptr, *y1 = nullptr, *alpha = nullptr, *scal = nullptr;
     double *part = nullptr, *trace_out = nullptr;
+    double* tblk = nullptr;                    // Npad scratch vector (block right-hand sides of the sharded solves)
     int* info_dev = nullptr;
     int* flags = nullptr;                      // ready-flags of the single-launch triangular solves (2 x (Npad/128 + 1))
     int trsv_fused = 1;
@@ -112,7 +122,29 @@ struct gpb200_handle {
     int epoch = 0;
     int** peer_sig_dev = nullptr;              // device array: &peer_sig[q][rank]
     bool push_panel = false;                   // set while the owner factors a panel: leaf + leaf TRSM also store to the peers
+    // ---- row-sharded storage (shard_impl.cuh): F / G are virtual address ranges, physical pages exist for owned rows only ----
+    int shard_opt = -1;                        // option "shard": -1 auto (when replicated F+G would not fit), 0 never, 1 always
+    int shard_rb_opt = 0;                      // option "shard_rb": ownership block in 128-row tiles (0 = auto)
+    bool sharded = false;                      // current storage mode of F / G
+    int rb = 4;                                // effective ownership block (tiles); panel width NBp = 128 * rb
+    int row_lim = 0;                           // chol_panel: rows below this limit only (diagonal block of a sharded panel); 0 = Npad
+    VmBuf vmF, vmG;
+    double* P[2] = {nullptr, nullptr};         // panel buffers, Npad x NBp (global row order); P[1] doubles as the NBp x Npad row panel
+    double* Sbuf = nullptr;                    // all-gather staging: nranks regions of S_per_rank doubles; scratch of the inverse sweep
+    size_t S_per_rank = 0;
+    CUtensorMap mapP[2] = {}, mapXR{}, mapS{};
+    double* red = nullptr;                     // small reduction scratch (local group all-reduce)
+    int* redi = nullptr;
+    struct gpb200_group* grp = nullptr;        // in-process group of virtual ranks on one device (gpb200_group_create)
+    std::vector<cudaEvent_t> evring;
+    size_t evring_next = 0;
     std::string err;
+};
+
+// in-process "communicator": R handles on one device acting as R ranks of the sharded schedules, driven in lock step by
+// one host thread.  Collectives are device-to-device copies ordered by events (shard_impl.cuh).
+struct gpb200_group {
+    std::vector<gpb200_handle*> hs;
 };
 
 
@@ -151,6 +183,8 @@ struct NcclApi {
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     bool ok = false;
 } g_nccl;
 
@@ -167,8 +201,10 @@ bool nccl_load() {
     g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(L, "ncclAllGather");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(L, "ncclAllReduce");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(L, "ncclGetErrorString");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(L, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(L, "ncclGroupEnd");
     g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.Broadcast &&
-                g_nccl.AllGather && g_nccl.AllReduce && g_nccl.GetErrorString;
+                g_nccl.AllGather && g_nccl.AllReduce && g_nccl.GetErrorString && g_nccl.GroupStart && g_nccl.GroupEnd;
     return g_nccl.ok;
 }
 
@@ -214,10 +250,13 @@ void close_peer_maps(gpb200_handle* h) {
     h->p2p = false; h->n_peer = 0;
 }
 
+void free_FG(gpb200_handle* h);               // shard_impl.cuh: F / G are cudaMalloc'ed (replicated) or VMM ranges (row-sharded)
+
 void free_data(gpb200_handle* h) {
-    double** ptrs[] = {&h->x, &h->F, &h->G, &h->Dinv, &h->DinvT, &h->logd, &h->noise_var, &h->r0, &h->r1,
+    free_FG(h);
+    double** ptrs[] = {&h->x, &h->Dinv, &h->DinvT, &h->logd, &h->noise_var, &h->r0, &h->r1,
                        &h->y1, &h->alpha, &h->scal, &h->part, &h->trace_out, &h->xs, &h->Kst, &h->Kss,
-                       &h->pmu, &h->pvar, &h->pkdiag};
+                       &h->pmu, &h->pvar, &h->pkdiag, &h->tblk};
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
     if (h->flags) { cudaFree(h->flags); h->flags = nullptr; }
@@ -247,11 +286,12 @@ double gemm_exec_flops(const GemmDesc& d) {
         if (Mz <= 0 || Nz <= 0 || Kz <= 0) continue;
         const int tm = Mz / TILE, tn = Nz / TILE;
         for (int bm = 0; bm < tm; ++bm) {
-            if (d.bm_mod > 1 && (bm % d.bm_mod) != d.bm_rem) continue;
+            if (d.bm_mod > 1 && (((bm + d.bm_off) / (d.bm_div > 0 ? d.bm_div : 1)) % d.bm_mod) != d.bm_rem) continue;
             const int bn_hi = (d.flags & GEMM_LOWER_ONLY) ? std::min(bm + 1, tn) : tn;
             for (int bn = 0; bn < bn_hi; ++bn) {
-                if (d.bn_mod > 1 && (bn % d.bn_mod) != d.bn_rem) continue;
-                int lo = (d.flags & GEMM_KLO_M) ? bm * TILE : 0;
+                if (d.bn_mod > 1 && (((bn + d.bn_off) / (d.bn_div > 0 ? d.bn_div : 1)) % d.bn_mod) != d.bn_rem) continue;
+                int lo = (d.flags & GEMM_KLO_M) ? d.klo_off + bm * TILE : 0;
+                if (d.flags & GEMM_KLO_N) lo = std::max(lo, bn * TILE);
                 int hi = Kz;
                 if (d.flags & GEMM_KHI_M) hi = std::min(hi, (bm + 1) * TILE);
                 if (d.flags & GEMM_KHI_N) hi = std::min(hi, (bn + 1) * TILE);
@@ -373,7 +413,7 @@ cudaError_t leaf_launch(gpb200_handle* h, int p, cudaStream_t st) {
 // that leaf run on a high-priority side stream while the main stream does the rest of the update -- the
 // 125 us latency-bound leaf disappears behind the GEMM.
 cudaError_t chol_panel(gpb200_handle* h, int p, int n, int s, bool leaf_done = false) {
-    const int Np = (int)h->Npad;
+    const int Np = h->row_lim > 0 ? h->row_lim : (int)h->Npad;
     cudaError_t e;
     if (s == TILE) {
         if (leaf_done) e = cudaStreamWaitEvent(h->st, h->ev_la2, 0);
@@ -877,6 +917,32 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
+#include "shard_impl.cuh"
+
+// collective entry points of a sharded handle: in an in-process group they must be called on the leader (it drives every
+// virtual rank); per-rank state (host arguments) is replicated to every local handle here
+int shard_entry(gpb200_handle* h, Locals& L) {
+    L = locals(h);
+    if (h->grp && L[0] != h) return fail(h, GPB200_ESTATE, "in-process group: call collective entry points on the leader (rank 0) handle");
+    return GPB200_OK;
+}
+// debug getters with sharded storage: rows this rank owns, zeros elsewhere (the caller adds the ranks' pieces)
+int copy_own_rows(gpb200_handle* h, double* dst_host, const double* src_dev) {
+    const int64_t N = h->N;
+    memset(dst_host, 0, sizeof(double) * (size_t)N * (size_t)N);
+    for (int64_t t = 0; t * TILE < N; ++t) {
+        if (owner_of_tile(h, t) != h->rank) continue;
+        const int64_t r0 = t * TILE, nr = std::min<int64_t>(TILE, N - r0);
+        CK(cudaMemcpy2DAsync(dst_host + r0 * N, sizeof(double) * N, src_dev + r0 * h->ld, sizeof(double) * h->ld, sizeof(double) * N, nr,
+                             cudaMemcpyDeviceToHost, h->st));
+    }
+    return GPB200_OK;
+}
+int sync_all(const Locals& L) {
+    for (auto* q : L) SCK(q, cudaStreamSynchronize(q->st));
+    return GPB200_OK;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -931,8 +997,15 @@ int gpb200_create(gpb200_handle** out, int device) {
 void gpb200_destroy(gpb200_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->grp) {                              // a group dissolves with its first destroyed member
+        gpb200_group* g = h->grp;
+        for (auto* m : g->hs) { if (m->st) cudaStreamSynchronize(m->st); }
+        for (auto* m : g->hs) { m->grp = nullptr; m->factored = m->inv_ready = false; }
+        delete g;
+    }
     if (h->st) cudaStreamSynchronize(h->st);
     free_data(h);
+    for (auto e : h->evring) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
@@ -968,6 +1041,14 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
         h->dist_nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "shard")) {                // storage of F / G with several ranks: -1 auto, 0 replicated, 1 row-sharded
+        if (value < -1 || value > 1) return fail(h, GPB200_EINVAL, "shard must be -1 (auto), 0 or 1");
+        h->shard_opt = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
+    }
+    if (!strcmp(key, "shard_rb")) {             // ownership block of the row-sharded storage in 128-row tiles (panel = 128 * rb)
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(h, GPB200_EINVAL, "shard_rb must be 0 (auto), 1, 2, 4 or 8");
+        h->shard_rb_opt = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
+    }
     if (!strcmp(key, "trsv_fused")) { h->trsv_fused = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "p2p")) {                 // 0: NCCL panel broadcast even if peer memory is mapped
         if (value && h->n_peer == 0) return fail(h, GPB200_ESTATE, "p2p: ipc_import first");
@@ -1015,15 +1096,12 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
     if (realloc) {
         free_data(h);
         h->N = N; h->Npad = Npad; h->ld = Npad; h->d = d;
-        const size_t nn = sizeof(double) * (size_t)Npad * (size_t)Npad;
         CK(cudaMalloc(&h->x, sizeof(double) * Npad * d));      // Npad rows: N may grow up to Npad without realloc
-        CK(cudaMalloc(&h->F, nn));
-        CK(cudaMalloc(&h->G, nn));
         CK(cudaMalloc(&h->Dinv, sizeof(double) * Npad * TILE));
         CK(cudaMalloc(&h->DinvT, sizeof(double) * Npad * TILE));
         const size_t nv = sizeof(double) * Npad;
         CK(cudaMalloc(&h->logd, nv)); CK(cudaMalloc(&h->noise_var, nv)); CK(cudaMalloc(&h->r0, nv));
-        CK(cudaMalloc(&h->r1, nv)); CK(cudaMalloc(&h->y1, nv)); CK(cudaMalloc(&h->alpha, nv));
+        CK(cudaMalloc(&h->r1, nv)); CK(cudaMalloc(&h->y1, nv)); CK(cudaMalloc(&h->alpha, nv)); CK(cudaMalloc(&h->tblk, nv));
         CK(cudaMalloc(&h->scal, sizeof(double) * 16));
         CK(cudaMalloc(&h->info_dev, sizeof(int)));
         CK(cudaMalloc(&h->flags, sizeof(int) * 2 * (Npad / TILE + 1)));
@@ -1037,12 +1115,10 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
         const int64_t T = Npad / TILE;
         CK(cudaMalloc(&h->part, sizeof(double) * (size_t)(T * (T + 1) / 2) * (GPB200_MAX_THETA + 1)));
         CK(cudaMalloc(&h->trace_out, sizeof(double) * (GPB200_MAX_THETA + 1)));
-        CK(cudaMemsetAsync(h->F, 0, nn, h->st));
-        CK(cudaMemsetAsync(h->G, 0, nn, h->st));
-        h->tma_ok = gemm_make_tensor_map(&h->mapF, h->F, Npad, Npad, Npad) &&
-                    gemm_make_tensor_map(&h->mapG, h->G, Npad, Npad, Npad) &&
-                    gemm_make_tensor_map(&h->mapDinv, h->Dinv, Npad, TILE, TILE) &&
-                    gemm_make_tensor_map(&h->mapDinvT, h->DinvT, Npad, TILE, TILE);
+        // F / G: replicated (cudaMalloc) or row-sharded (virtual range, owned rows mapped) -- decided by the communicator,
+        // the problem size and option "shard"; re-checked at every factorize (the communicator may be joined later)
+        int rc_fg = ensure_storage(h);
+        if (rc_fg != GPB200_OK) return rc_fg;
     }
     h->N = N;
     // x arrives as Julia's d x N column-major (ld = ldx): point i is the contiguous run x[i*ldx .. +d)
@@ -1121,17 +1197,51 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
         if (!isfinite(theta[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite hyper-parameter");
     CK(cudaSetDevice(h->device));
     h->factored = h->inv_ready = h->alpha_ready = false;
-    for (int i = 0; i < h->prog.n_theta; ++i) h->theta[i] = theta[i];
-    kprog_set_theta(h->prog, theta);
     std::vector<double> nv((size_t)n_noise);
     for (int64_t i = 0; i < n_noise; ++i) {
         if (!isfinite(log_noise[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite logNoise");
         nv[i] = exp(2.0 * log_noise[i]);
     }
-    CK(cudaMemcpyAsync(h->noise_var, nv.data(), sizeof(double) * n_noise, cudaMemcpyHostToDevice, h->st));
-    h->n_noise = n_noise; h->nugget = extra_nugget;
+    Locals L;
+    { int rc = shard_entry(h, L); if (rc) return rc; }
+    for (auto* q : L) { int rc = ensure_storage(q); if (rc) { if (q != h) h->err = q->err; return rc; } }
     const int init = INT_MAX;
-    CK(cudaMemcpyAsync(h->info_dev, &init, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    for (auto* q : L) {                                    // (an in-process group: every virtual rank gets the arguments)
+        if (!q->has_data || !q->has_kernel || q->prog.n_theta != h->prog.n_theta || q->N != h->N)
+            return fail(h, GPB200_ESTATE, "factorize: every handle of the group needs the same set_data / set_kernel");
+        q->factored = q->inv_ready = q->alpha_ready = false;
+        for (int i = 0; i < q->prog.n_theta; ++i) q->theta[i] = theta[i];
+        kprog_set_theta(q->prog, theta);
+        SCK(q, cudaMemcpyAsync(q->noise_var, nv.data(), sizeof(double) * n_noise, cudaMemcpyHostToDevice, q->st));
+        q->n_noise = n_noise; q->nugget = extra_nugget;
+        SCK(q, cudaMemcpyAsync(q->info_dev, &init, sizeof(int), cudaMemcpyHostToDevice, q->st));
+    }
+    if (h->sharded) {
+        // row-sharded storage: own rows of the Gram matrix, then the all-gathered-panel Cholesky (shard_impl.cuh)
+        CK(cudaEventRecord(h->ev0, h->st));
+        for (auto* q : L) {
+            ++q->launches;
+            SCK(q, gram_lower_launch(q->prog, q->x, q->d, q->d, q->N, q->Npad, q->noise_var, n_noise, extra_nugget, q->G, q->ld,
+                                     q->st, q->rb, q->nranks, q->rank, 1));
+        }
+        CK(cudaEventRecord(h->ev1, h->st));
+        { int rc = shard_cholesky(L); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
+        CK(cudaEventRecord(h->ev2, h->st));
+        int info_s = 0;
+        CK(cudaMemcpyAsync(&info_s, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        { int rc = sync_all(L); if (rc) return rc; }
+        for (auto* q : L) profile_collect(q);
+        h->ms[0] = ev_ms(h->ev0, h->ev1);
+        h->ms[1] = ev_ms(h->ev1, h->ev2);
+        if (info_s != INT_MAX) {
+            char buf[128];
+            snprintf(buf, sizeof buf, "matrix is not positive definite; leading minor %d", info_s);
+            h->err = buf;
+            return info_s > h->N ? (int)h->N : info_s;
+        }
+        for (auto* q : L) q->factored = true;
+        return GPB200_OK;
+    }
 
     CK(cudaEventRecord(h->ev0, h->st));
     ++h->launches;
@@ -1186,6 +1296,14 @@ int gpb200_solve(gpb200_handle* h, const double* rhs, double* out) {
     if (!h || !rhs || !out) return GPB200_EINVAL;
     if (!h->factored) return fail(h, GPB200_ESTATE, "solve: factorize first");
     CK(cudaSetDevice(h->device));
+    if (h->sharded) {
+        Locals L;
+        { int rc = shard_entry(h, L); if (rc) return rc; }
+        for (auto* q : L) { int rc = upload_padded(q, q->r1, rhs); if (rc) return rc; }
+        { int rc = shard_solve(L, &gpb200_handle::r1, &gpb200_handle::y1, &gpb200_handle::r0); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
+        CK(cudaMemcpyAsync(out, h->r0, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
+        return sync_all(L);
+    }
     int rc = upload_padded(h, h->r1, rhs);
     if (rc) return rc;
     CK(solve_device(h, h->r1, h->y1, h->r0));
@@ -1199,10 +1317,19 @@ int gpb200_mll(gpb200_handle* h, const double* y_minus_mean, double* alpha, doub
     if (!h->factored) return fail(h, GPB200_ESTATE, "mll: factorize first");
     CK(cudaSetDevice(h->device));
     CK(cudaEventRecord(h->ev0, h->st));
+    Locals Ls;
+    if (h->sharded) { int rc = shard_entry(h, Ls); if (rc) return rc; }
     int rc = upload_padded(h, h->r0, y_minus_mean);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->r1, h->r0, sizeof(double) * h->Npad, cudaMemcpyDeviceToDevice, h->st));
-    CK(solve_device(h, h->r1, h->y1, h->alpha));
+    if (h->sharded) {
+        for (auto* q : Ls) if (q != h) { rc = upload_padded(q, q->r0, y_minus_mean); if (rc) return rc; }
+        rc = shard_solve(Ls, &gpb200_handle::r0, &gpb200_handle::y1, &gpb200_handle::alpha);
+        if (rc) { if (Ls[0] != h) h->err = Ls[0]->err; return rc; }
+        for (auto* q : Ls) q->alpha_ready = true;
+    } else {
+        CK(cudaMemcpyAsync(h->r1, h->r0, sizeof(double) * h->Npad, cudaMemcpyDeviceToDevice, h->st));
+        CK(solve_device(h, h->r1, h->y1, h->alpha));
+    }
     h->launches += 2;
     CK(dot_launch(h->r0, h->alpha, h->Npad, h->scal + 0, h->st));
     CK(sum_launch(h->logd, h->Npad, h->scal + 1, h->st));
@@ -1211,8 +1338,9 @@ int gpb200_mll(gpb200_handle* h, const double* y_minus_mean, double* alpha, doub
     if (alpha) CK(cudaMemcpyAsync(alpha, h->alpha, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
     CK(cudaEventRecord(h->ev1, h->st));
     CK(cudaStreamSynchronize(h->st));
+    if (h->sharded) { int rcs = sync_all(Ls); if (rcs) return rcs; }
     h->ms[2] = ev_ms(h->ev0, h->ev1);
-    { int rcw = check_trsv_watchdog(h); if (rcw) return rcw; }
+    if (!h->sharded) { int rcw = check_trsv_watchdog(h); if (rcw) return rcw; }
     *mll = -(s[0] + s[1] + LOG2PI * (double)h->N) / 2.0;    // src/GPE.jl:210
     h->alpha_ready = true;
     return GPB200_OK;
@@ -1224,6 +1352,16 @@ int gpb200_grad_prepare(gpb200_handle* h) {
     if (h->inv_ready) return GPB200_OK;
     CK(cudaSetDevice(h->device));
     CK(cudaEventRecord(h->ev0, h->st));
+    if (h->sharded) {
+        Locals L;
+        { int rc = shard_entry(h, L); if (rc) return rc; }
+        { int rc = shard_inverse(L); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
+        CK(cudaEventRecord(h->ev1, h->st));
+        { int rc = sync_all(L); if (rc) return rc; }
+        for (auto* q : L) { profile_collect(q); q->inv_ready = true; }
+        h->ms[3] = ev_ms(h->ev0, h->ev1);
+        return GPB200_OK;
+    }
     if (h->nranks > 1) { int rc = inverse_dist(h); if (rc) return rc; }
     else CK(inverse_from_factor(h));
     CK(cudaEventRecord(h->ev1, h->st));
@@ -1239,16 +1377,31 @@ int gpb200_grad_kernel(gpb200_handle* h, const double* alpha, double* dmll_kerne
     if (!h->inv_ready) return fail(h, GPB200_ESTATE, "grad_kernel: grad_prepare first");
     if (!alpha && !h->alpha_ready) return fail(h, GPB200_ESTATE, "grad_kernel: no alpha (call mll or pass alpha)");
     CK(cudaSetDevice(h->device));
+    Locals Lg;
+    if (h->sharded) { int rc = shard_entry(h, Lg); if (rc) return rc; } else Lg = Locals{h};
     if (alpha) {
-        int rc = upload_padded(h, h->alpha, alpha);
-        if (rc) return rc;
-        h->alpha_ready = true;
+        for (auto* q : Lg) {
+            int rc = upload_padded(q, q->alpha, alpha);
+            if (rc) return rc;
+            q->alpha_ready = true;
+        }
     }
     CK(cudaEventRecord(h->ev0, h->st));
+    if (h->sharded) {
+        // fused trace over the own rows of K^-1 (block-cyclic tile rows), P+1 partial sums summed over the ranks
+        for (auto* q : Lg) {
+            q->launches += 2;
+            SCK(q, trace_launch(q->prog, q->x, q->d, q->d, q->N, q->Npad, q->alpha, q->G, q->ld, q->part, q->trace_out, q->st,
+                                q->nranks, q->rank, q->rb));
+        }
+        int rc = coll_allreduce_sum(Lg, [&](gpb200_handle* q) { return q->trace_out; }, (size_t)trace_num_acc(h->prog));
+        if (rc) { if (Lg[0] != h) h->err = Lg[0]->err; return rc; }
+    } else {
     h->launches += 2;
     CK(trace_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
                     h->nranks, h->rank));
-    if (h->nranks > 1) {                                   // P+1 partial sums, summed over ranks
+    }
+    if (!h->sharded && h->nranks > 1) {                    // P+1 partial sums, summed over ranks
         CK(cudaEventRecord(h->ev_x, h->st));
         CK(cudaStreamWaitEvent(h->st_comm, h->ev_x, 0));
         CKN(g_nccl.AllReduce(h->trace_out, h->trace_out, (size_t)trace_num_acc(h->prog), ncclDouble, ncclSum, h->comm, h->st_comm));
@@ -1260,6 +1413,7 @@ int gpb200_grad_kernel(gpb200_handle* h, const double* alpha, double* dmll_kerne
     std::vector<double> out((size_t)np + 1);
     CK(cudaMemcpyAsync(out.data(), h->trace_out, sizeof(double) * (np + 1), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    if (h->sharded) { int rcs = sync_all(Lg); if (rcs) return rcs; }
     h->ms[4] = ev_ms(h->ev0, h->ev1);
     if (dmll_kernel) for (int p = 0; p < np; ++p) dmll_kernel[p] = out[p];
     if (trA) *trA = out[np];
@@ -1285,10 +1439,46 @@ int gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, 
         if (v >= TILE && v < cap) cap = v;
     }
     if (cap < TILE) cap = TILE;
+    if (h->sharded && cap > h->Npad) cap = h->Npad;       // a block of V' travels through the Npad x NBp panel buffer
     if (cov) cap = (M + TILE - 1) / TILE * TILE;          // full covariance needs all of V at once
+    if (cov && h->sharded && cap > h->Npad) return fail(h, GPB200_EINVAL, "predict: full covariance of more than Npad test points is not supported with sharded storage");
     const bool need_v = (var != nullptr) || (cov != nullptr);
+    Locals Lp;
+    if (h->sharded) {
+        int rc = shard_entry(h, Lp); if (rc) return rc;
+        if (alpha) for (auto* q : Lp) if (q != h) { rc = upload_padded(q, q->alpha, alpha); if (rc) return rc; }
+    }
     CK(cudaEventRecord(h->ev2, h->st));
-    for (int64_t m0 = 0; m0 < M; m0 += cap) {
+    for (int64_t m0 = 0; h->sharded && m0 < M; m0 += cap) {
+        // row-sharded factor: K*' on every rank, the triangular solve runs over column blocks owned like the rows of L
+        const int64_t Mc = (M - m0 < cap) ? M - m0 : cap;
+        const int64_t Mpad = (Mc + TILE - 1) / TILE * TILE;
+        for (auto* q : Lp) {
+            int rc = ensure_predict_ws(q, Mc, cov != nullptr);
+            if (rc) { if (q != h) h->err = q->err; return rc; }
+            SCK(q, cudaMemcpy2DAsync(q->xs, sizeof(double) * q->d, xs + m0 * ldxs, sizeof(double) * ldxs, sizeof(double) * q->d, Mc,
+                                     cudaMemcpyHostToDevice, q->st));
+            ++q->launches;
+            SCK(q, crossgram_launch(q->prog, q->xs, q->d, Mc, Mpad, q->x, q->d, q->N, q->Npad, q->d, q->Kst, q->Npad, q->st));
+            if (need_v) {
+                ++q->launches;
+                SCK(q, kdiag_launch(q->prog, q->xs, q->d, Mc, q->pvar, q->st));           // running variance starts at k**
+                if (cov) { ++q->launches; SCK(q, gram_full_launch(q->prog, q->xs, q->d, Mc, Mpad, q->d, q->Kss, Mpad, q->st)); }
+            }
+        }
+        ++h->launches;
+        CK(rowdot_launch(h->Kst, h->Npad, h->alpha, Mc, h->Npad, h->pmu, h->st));          // GP.jl:26
+        CK(cudaMemcpyAsync(mu + m0, h->pmu, sizeof(double) * Mc, cudaMemcpyDeviceToHost, h->st));
+        if (need_v) {
+            int rc = shard_predict_solve(Lp, (int)Mpad, Mc, var != nullptr, cov != nullptr);
+            if (rc) { if (Lp[0] != h) h->err = Lp[0]->err; return rc; }
+            if (var) CK(cudaMemcpyAsync(var + m0, h->pvar, sizeof(double) * Mc, cudaMemcpyDeviceToHost, h->st));
+            if (cov) CK(cudaMemcpy2DAsync(cov, sizeof(double) * M, h->Kss, sizeof(double) * Mpad, sizeof(double) * M, M,
+                                          cudaMemcpyDeviceToHost, h->st));
+        }
+        { int rc = sync_all(Lp); if (rc) return rc; }
+    }
+    for (int64_t m0 = 0; !h->sharded && m0 < M; m0 += cap) {
         const int64_t Mc = (M - m0 < cap) ? M - m0 : cap;
         const int64_t Mpad = (Mc + TILE - 1) / TILE * TILE;
         int rc = ensure_predict_ws(h, Mc, cov != nullptr);
@@ -1356,6 +1546,8 @@ int gpb200_get_factor(gpb200_handle* h, double* U) {
     if (!h->factored) return fail(h, GPB200_ESTATE, "get_factor: factorize first");
     CK(cudaSetDevice(h->device));
     const int64_t N = h->N;
+    if (h->sharded) { int rc = copy_own_rows(h, U, h->F); if (rc) return rc; }
+    else
     CK(cudaMemcpy2DAsync(U, sizeof(double) * N, h->F, sizeof(double) * h->ld, sizeof(double) * N, N,
                          cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -1368,9 +1560,11 @@ int gpb200_get_factor(gpb200_handle* h, double* U) {
 int gpb200_get_inverse(gpb200_handle* h, double* Kinv) {
     if (!h || !Kinv) return GPB200_EINVAL;
     if (!h->inv_ready) return fail(h, GPB200_ESTATE, "get_inverse: grad_prepare first");
-    if (h->nranks > 1) return fail(h, GPB200_ESTATE, "get_inverse: K^-1 is distributed over the ranks (tile rows round-robin)");
+    if (h->nranks > 1 && !h->sharded) return fail(h, GPB200_ESTATE, "get_inverse: K^-1 is distributed over the ranks (tile rows round-robin)");
     CK(cudaSetDevice(h->device));
     const int64_t N = h->N;
+    if (h->sharded) { int rc = copy_own_rows(h, Kinv, h->G); if (rc) return rc; }     // own rows only (others zero): sum over the ranks
+    else
     CK(cudaMemcpy2DAsync(Kinv, sizeof(double) * N, h->G, sizeof(double) * h->ld, sizeof(double) * N, N,
                          cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -1382,7 +1576,7 @@ int gpb200_get_inverse(gpb200_handle* h, double* Kinv) {
 int gpb200_get_inverse_diag(gpb200_handle* h, double* diag) {
     if (!h || !diag) return GPB200_EINVAL;
     if (!h->inv_ready) return fail(h, GPB200_ESTATE, "get_inverse_diag: grad_prepare first");
-    if (h->nranks > 1) return fail(h, GPB200_ESTATE, "get_inverse_diag: K^-1 is distributed over the ranks (tile rows round-robin)");
+    if (h->nranks > 1) return fail(h, GPB200_ESTATE, "get_inverse_diag: K^-1 is distributed over the ranks");
     CK(cudaSetDevice(h->device));
     // strided gather of G[i,i]: pitch (ld+1) doubles, one double per row
     CK(cudaMemcpy2DAsync(diag, sizeof(double), h->G, sizeof(double) * (h->ld + 1), sizeof(double), h->N,
@@ -1507,6 +1701,37 @@ int gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128) 
     return GPB200_OK;
 }
 
+
+int gpb200_storage_info(gpb200_handle* h, int64_t* out, int32_t n) {
+    if (!h || !out) return GPB200_EINVAL;
+    int64_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    v[6] = h->tma_ok ? 1 : 0;
+    v[0] = h->sharded ? 1 : 0;
+    v[1] = h->sharded ? (int64_t)vm_mapped_bytes(h->vmF) : (h->F ? (int64_t)sizeof(double) * h->Npad * h->Npad : 0);
+    v[2] = h->sharded ? (int64_t)vm_mapped_bytes(h->vmG) : (h->G ? (int64_t)sizeof(double) * h->Npad * h->Npad : 0);
+    v[3] = h->sharded ? h->rb : 0;
+    v[4] = h->nranks;
+    v[5] = h->rank;
+    for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+    return GPB200_OK;
+}
+
+int gpb200_group_create(gpb200_handle** hs, int n) {
+    if (!hs || n < 1 || n > 8) return GPB200_EINVAL;
+    for (int i = 0; i < n; ++i) {
+        if (!hs[i]) return GPB200_EINVAL;
+        if (hs[i]->grp || hs[i]->comm) return fail(hs[i], GPB200_ESTATE, "group_create: handle already belongs to a group / communicator");
+        if (hs[i]->device != hs[0]->device) return fail(hs[i], GPB200_EINVAL, "group_create: all handles must live on one device");
+        for (int j = 0; j < i; ++j) if (hs[j] == hs[i]) return fail(hs[i], GPB200_EINVAL, "group_create: duplicate handle");
+    }
+    gpb200_group* g = new gpb200_group();
+    for (int i = 0; i < n; ++i) {
+        g->hs.push_back(hs[i]);
+        hs[i]->grp = g; hs[i]->nranks = n; hs[i]->rank = i;
+        hs[i]->factored = hs[i]->inv_ready = false;
+    }
+    return GPB200_OK;
+}
 
 // ================================================================================================
 // FITC -- Fully Independent Training Conditional (src/sparse/fully_indep_train_conditional.jl)

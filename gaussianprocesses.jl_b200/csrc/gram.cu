@@ -38,10 +38,11 @@ __global__ void __launch_bounds__(NT) gram_lower_kernel(const __grid_constant__ 
                                                         long long ldx, int d, long long N, long long Npad,
                                                         const double* __restrict__ noise_var, long long n_noise,
                                                         double nugget, double* __restrict__ G, long long ldg,
-                                                        int own_tiles, int nranks, int rank) {
+                                                        int own_tiles, int nranks, int rank, int own_axis) {
     const int bm = blockIdx.y, bn = blockIdx.x;
     if (bn > bm) return;
-    if (own_tiles > 0 && ((bn / own_tiles) % nranks) != rank) return;    // block-column ownership (multi-GPU)
+    // multi-GPU ownership: block columns (replicated storage, own_axis 0) or block rows (row-sharded storage, own_axis 1)
+    if (own_tiles > 0 && (((own_axis ? bm : bn) / own_tiles) % nranks) != rank) return;
     extern __shared__ double sm[];
     const int ds = d | 1;
     double* sXi = sm;
@@ -234,7 +235,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(NT) trace_kernel(const __grid_constant__ KProg P, const double* __restrict__ x,
                                                    long long ldx, int d, long long N, const double* __restrict__ alpha,
                                                    const double* __restrict__ Kinv, long long ldg,
-                                                   double* __restrict__ part, int tiles, int bm_mod, int bm_rem) {
+                                                   double* __restrict__ part, int tiles, int bm_mod, int bm_rem, int bm_div) {
     // triangular tile index
     const int lin = blockIdx.x;
     int bm = (int)((sqrt(8.0 * (double)lin + 1.0) - 1.0) * 0.5);
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(NT) trace_kernel(const __grid_constant__ KProg
     while ((bm + 1) * (bm + 2) / 2 <= lin) ++bm;
     const int bn = lin - bm * (bm + 1) / 2;
     const int np = P.n_theta;
-    if (bm_mod > 1 && (bm % bm_mod) != bm_rem) {            // tile row owned by another rank
+    if (bm_mod > 1 && ((bm / bm_div) % bm_mod) != bm_rem) {  // tile row owned by another rank
         const int na = FAST ? 3 : np + 1;
         for (int p = threadIdx.x; p < na; p += NT) part[(long long)lin * na + p] = 0.0;
         return;
@@ -435,17 +436,17 @@ cudaError_t ensure_smem(K kern, size_t bytes) {
 
 cudaError_t gram_lower_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad,
                               const double* noise_var, int64_t n_noise, double nugget, double* G, int64_t ldg,
-                              cudaStream_t st, int own_tiles, int nranks, int rank) {
+                              cudaStream_t st, int own_tiles, int nranks, int rank, int own_axis) {
     const int T = (int)(Npad / TB);
     dim3 grid(T, T);
     const size_t sm = xtile_smem(d);
     cudaError_t e;
     if (P.fast) {
         if ((e = ensure_smem(gram_lower_kernel<true>, sm)) != cudaSuccess) return e;
-        gram_lower_kernel<true><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank);
+        gram_lower_kernel<true><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis);
     } else {
         if ((e = ensure_smem(gram_lower_kernel<false>, sm)) != cudaSuccess) return e;
-        gram_lower_kernel<false><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank);
+        gram_lower_kernel<false><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis);
     }
     return cudaGetLastError();
 }
@@ -489,7 +490,8 @@ int trace_num_acc(const KProg& P) { return P.fast ? 3 : P.n_theta + 1; }
 
 cudaError_t trace_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad,
                          const double* alpha, const double* Kinv, int64_t ldg, double* part, double* out,
-                         cudaStream_t st, int bm_mod, int bm_rem) {
+                         cudaStream_t st, int bm_mod, int bm_rem, int bm_div) {
+    if (bm_div < 1) bm_div = 1;
     const int T = (int)(Npad / TB);
     const int tiles = T * (T + 1) / 2;
     const int nacc = trace_num_acc(P);
@@ -497,10 +499,10 @@ cudaError_t trace_launch(const KProg& P, const double* x, int64_t ldx, int d, in
     cudaError_t e;
     if (P.fast) {
         if ((e = ensure_smem(trace_kernel<true>, sm)) != cudaSuccess) return e;
-        trace_kernel<true><<<tiles, NT, sm, st>>>(P, x, ldx, d, N, alpha, Kinv, ldg, part, tiles, bm_mod, bm_rem);
+        trace_kernel<true><<<tiles, NT, sm, st>>>(P, x, ldx, d, N, alpha, Kinv, ldg, part, tiles, bm_mod, bm_rem, bm_div);
     } else {
         if ((e = ensure_smem(trace_kernel<false>, sm)) != cudaSuccess) return e;
-        trace_kernel<false><<<tiles, NT, sm, st>>>(P, x, ldx, d, N, alpha, Kinv, ldg, part, tiles, bm_mod, bm_rem);
+        trace_kernel<false><<<tiles, NT, sm, st>>>(P, x, ldx, d, N, alpha, Kinv, ldg, part, tiles, bm_mod, bm_rem, bm_div);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     reduce_partials_kernel<<<nacc, 256, 0, st>>>(part, tiles, nacc, out);

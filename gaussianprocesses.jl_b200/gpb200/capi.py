@@ -65,6 +65,8 @@ _SIGNATURES = {
     "gpb200_fitc_set_mode": (C.c_int, [_H, C.c_int]),
     "gpb200_fitc_launch_count": (C.c_int64, [_H]),
     "gpb200_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
+    "gpb200_group_create": (C.c_int, [C.POINTER(_H), C.c_int]),
+    "gpb200_storage_info": (C.c_int, [_H, C.POINTER(C.c_int64), C.c_int32]),
 }
 
 _lib = None
@@ -234,6 +236,18 @@ class Engine:
         self._check(self._lib.gpb200_get_inverse_diag(self._h, _as_dp(d)), "get_inverse_diag")
         return d
 
+    def storage_info(self):
+        v = (C.c_int64 * 8)()
+        self._check(self._lib.gpb200_storage_info(self._h, v, 8), "storage_info")
+        return dict(sharded=bool(v[0]), bytes_F=int(v[1]), bytes_G=int(v[2]), rb=int(v[3]), nranks=int(v[4]), rank=int(v[5]),
+                    tma=bool(v[6]))
+
+    def _own_rows_inverse(self):
+        """sharded storage: this rank's rows of K^-1 (lower part valid), zeros elsewhere"""
+        K = np.empty((self.N, self.N))
+        self._check(self._lib.gpb200_get_inverse(self._h, _as_dp(K)), "get_inverse")
+        return np.tril(K)
+
     def timings(self):
         ms = np.zeros(12)
         self._check(self._lib.gpb200_get_timings(self._h, _as_dp(ms), 12), "get_timings")
@@ -380,3 +394,81 @@ class FitcEngine:
 
     def launch_count(self):
         return int(self._lib.gpb200_fitc_launch_count(self._h))
+
+
+class LocalGroupEngine:
+    """R engines on ONE device acting as the R ranks of the ROW-SHARDED multi-GPU schedules (gpb200_group_create,
+    csrc/shard_impl.cuh): each virtual rank maps only its own block rows of the N x N factor / inverse, collectives are
+    event-ordered device copies.  Same interface as `Engine`, so `GPE(..., engine=LocalGroupEngine(4))` runs the whole
+    host mirror over the sharded storage on a single GPU (tests; the production path is one process per GPU + NCCL)."""
+
+    def __init__(self, nranks, device=0, rb=0):
+        self.engines = [Engine(device) for _ in range(int(nranks))]
+        self.lead = self.engines[0]
+        arr = (_H * len(self.engines))(*[e._h for e in self.engines])
+        rc = self.lead._lib.gpb200_group_create(arr, len(self.engines))
+        self.lead._check(rc, "group_create")
+        self.nranks = len(self.engines)
+        if rb:
+            self.set_option("shard_rb", rb)
+
+    # replicated state: every virtual rank gets it
+    def set_data(self, x_pm):
+        for e in self.engines:
+            e.set_data(x_pm)
+        self.N, self.d = self.lead.N, self.lead.d
+
+    def set_kernel(self, ops, dims, n_theta):
+        for e in self.engines:
+            e.set_kernel(ops, dims, n_theta)
+        self.n_theta = self.lead.n_theta
+
+    def set_option(self, key, value):
+        for e in self.engines:
+            e.set_option(key, value)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    # collective entry points: the leader drives every rank
+    def factorize(self, *a, **k):
+        return self.lead.factorize(*a, **k)
+
+    def mll(self, *a, **k):
+        return self.lead.mll(*a, **k)
+
+    def solve(self, *a, **k):
+        return self.lead.solve(*a, **k)
+
+    def logdet(self):
+        return self.lead.logdet()
+
+    def grad_prepare(self):
+        return self.lead.grad_prepare()
+
+    def grad_kernel(self, *a, **k):
+        return self.lead.grad_kernel(*a, **k)
+
+    def predict(self, *a, **k):
+        return self.lead.predict(*a, **k)
+
+    def timings(self):
+        return self.lead.timings()
+
+    def launch_count(self):
+        return sum(e.launch_count() for e in self.engines)
+
+    def gram(self):
+        return self.lead.gram()
+
+    # debug getters: every rank returns its own rows (zeros elsewhere); the pieces add up to the full matrix
+    def factor_upper(self):
+        return sum(e.factor_upper() for e in self.engines)
+
+    def inverse(self):
+        K = sum(e._own_rows_inverse() for e in self.engines)
+        return np.tril(K) + np.tril(K, -1).T
+
+    def inverse_diag(self):
+        return np.diag(self.inverse()).copy()

@@ -146,6 +146,9 @@ int64_t gpb200_launch_count(gpb200_handle* h);
  *   "profile"    1 = CUDA events around every GEMM launch (see gpb200_get_timings)
  *   "dist_nb"    multi-GPU: width of an owned block column, 0 = auto (~N/(8*ranks))
  *   "p2p"        multi-GPU: 1 = fused panel push over peer memory (after gpb200_ipc_import), 0 = NCCL broadcast
+ *   "shard"      multi-GPU storage of the two N x N buffers: 1 = row-sharded (each rank maps only its own block rows),
+ *                0 = replicated, -1 (default) = sharded only when the replicated form would not fit the device
+ *   "shard_rb"   row-sharded ownership block in 128-row tiles (panel width 128*rb): 0 auto, 1, 2, 4, 8
  * Returns GPB200_EINVAL for unknown keys or values.                                           */
 int  gpb200_set_option(gpb200_handle* h, const char* key, int64_t value);
 
@@ -179,6 +182,17 @@ int  gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128)
 #define GPB200_IPC_BYTES 512
 int  gpb200_ipc_export(gpb200_handle* h, char* out);
 int  gpb200_ipc_import(gpb200_handle* h, int nranks, const char* all_blobs);
+
+/* In-process group of `n` (<= 8) handles on ONE device acting as n ranks of the ROW-SHARDED schedules (the storage
+ * layout of config C4: each rank keeps only its own block rows of the N x N factor / inverse; see csrc/shard_impl.cuh).
+ * Collectives become event-ordered device copies, so a single-GPU box exercises exactly the multi-rank code.  Every
+ * handle needs the same gpb200_set_data / gpb200_set_kernel; factorize / mll / solve / grad_* / predict are then called
+ * on hs[0] only.  (One process per GPU uses gpb200_comm_init instead and option "shard".)                       */
+int  gpb200_group_create(gpb200_handle** hs, int n);
+/* storage of the two N x N buffers of this handle: out[0] = 1 if row-sharded, out[1] / out[2] = bytes of F / G physically
+ * backed on this device, out[3] = ownership block (tiles), out[4] = ranks, out[5] = rank, out[6] = 1 if the GEMMs run on
+ * TMA descriptors (0: plain-load fallback)  (cf. test/memory.jl:14-19)                                              */
+int  gpb200_storage_info(gpb200_handle* h, int64_t* out, int32_t n);
 
 /* ---- sparse FITC strategy (src/sparse/fully_indep_train_conditional.jl) ------------------------
  * FITC(x, Xu, y, mean, kern, logNoise) (fitc.jl:335-338) == GPE(..., FullyIndepStrat(Xu)).

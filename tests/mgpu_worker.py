@@ -43,6 +43,22 @@ def main():
             print("MGPU p2p and nccl paths disagree", gp.mll, t_p2p[0], flush=True)
             ok = False
         mu, s2 = gp.predict_f(Xs.T)
+        # the same problem on ROW-SHARDED storage (each rank maps only its own block rows; NCCL collectives)
+        ref = (gp.mll, gp.dmll.copy(), gp.alpha.copy(), mu.copy(), s2.copy())
+        gp._eng.set_option("shard", 1)
+        gp.update_target_and_dtarget()
+        mu_s, s2_s = gp.predict_f(Xs.T)
+        info = gp._eng.storage_info()
+        sh_ok = (info["sharded"] and abs(gp.mll - ref[0]) <= 1e-11 * abs(ref[0]) and np.allclose(gp.dmll, ref[1], rtol=1e-8, atol=1e-10)
+                 and np.max(np.abs(gp.alpha - ref[2])) <= 1e-10 * np.max(np.abs(ref[2]))
+                 and np.max(np.abs(mu_s - ref[3])) <= 1e-10 * np.max(np.abs(ref[3])) and np.max(np.abs(s2_s - ref[4])) <= 1e-10 * np.max(np.abs(ref[4])))
+        if not sh_ok:
+            print("MGPU rank %d: sharded storage disagrees with replicated: mll %.15g vs %.15g, info %s" % (rank, gp.mll, ref[0], info), flush=True)
+            ok = False
+        elif rank == 0:
+            print("MGPU world=%d N=%d: sharded (rb=%d, %.1f MB of F per rank) == replicated" % (world, N, info["rb"], info["bytes_F"] / 1e6), flush=True)
+        gp._eng.set_option("shard", 0)
+        gp.update_target_and_dtarget()
         if rank == 0:
             o = orc.mll_and_dmll(kern.spec(), X, y, -0.5, ("MeanConst", 0.2))
             mo, vo = orc.predict_f(kern.spec(), X, o, Xs, ("MeanConst", 0.2))
