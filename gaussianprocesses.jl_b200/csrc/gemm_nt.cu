@@ -405,6 +405,19 @@ bool gemm_make_tensor_map(CUtensorMap* out, const double* base, int64_t rows, in
     return r == CUDA_SUCCESS;
 }
 
+bool gemm_make_tensor_map_plain(CUtensorMap* out, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
+    memset(out, 0, sizeof(*out));
+    if (!g_encode) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     GemmKP p;
     p.A = d.A.buf.base; p.Asub = d.A.sub.base; p.B = d.B.buf.base; p.Bsub = d.B.sub.base;

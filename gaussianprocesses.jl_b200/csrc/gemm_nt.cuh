@@ -63,3 +63,8 @@ cudaError_t gemm_nt_init();
 // Build a TMA descriptor for a row-major [rows x cols] FP64 buffer, box 16 x 128, swizzle 128B.
 // Returns false (and leaves *out zeroed) if the driver entry point is unavailable.
 bool gemm_make_tensor_map(CUtensorMap* out, const double* base, int64_t rows, int64_t cols, int64_t ld);
+
+// Plain (un-swizzled) TMA descriptor of a row-major [rows x cols] FP64 buffer with a [box_rows x box_cols] box; rows past
+// `rows` are zero-filled by the hardware (used for the 128 x d input tiles of the Gram / trace kernels).
+// cols * 8 and ld * 8 must be multiples of 16 bytes.
+bool gemm_make_tensor_map_plain(CUtensorMap* out, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);

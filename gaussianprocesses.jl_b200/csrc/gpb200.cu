@@ -39,6 +39,7 @@
 #include "../../include/gpb200.h"
 #include "gemm_nt.cuh"
 #include "gram.cuh"
+#include "gram_fast.cuh"
 #include "kprog.cuh"
 #include "potrf_base.cuh"
 #include "shard_kernels.cuh"
@@ -72,6 +73,18 @@ struct gpb200_handle {
     double *noise_var = nullptr, *r0 = nullptr, *r1 = nullptr, *y1 = nullptr, *alpha = nullptr, *scal = nullptr;
     double *part = nullptr, *trace_out = nullptr;
     double* tblk = nullptr;                    // Npad scratch vector (block right-hand sides of the sharded solves)
+    // TMA-staged SEIso kernels (gram_fast.cu): inputs stored [Npad x dxp] with an even, zero-padded dxp <= 8
+    double* xp = nullptr;
+    int dxp = 0;
+    CUtensorMap mapX{};
+    bool xmap_ok = false;
+    int gram_fast = 1;                         // option "gram_fast": 0 = always the generic kernels of gram.cu
+    // posterior sampling (gpb200_rand): M x M sub-engine for chol(Sigma* + nugget I), normal draws / samples staging
+    gpb200_handle* sub = nullptr;
+    bool cov_keep_device = false;              // predict: leave the full covariance in Kss (no D2H)
+    double *rz = nullptr, *rout = nullptr;
+    int64_t rz_rows = 0, rz_cols = 0;
+    CUtensorMap mapRz{};
     int* info_dev = nullptr;
     int* flags = nullptr;                      // ready-flags of the single-launch triangular solves (2 x (Npad/128 + 1))
     int trsv_fused = 1;
@@ -256,7 +269,8 @@ void free_data(gpb200_handle* h) {
     free_FG(h);
     double** ptrs[] = {&h->x, &h->Dinv, &h->DinvT, &h->logd, &h->noise_var, &h->r0, &h->r1,
                        &h->y1, &h->alpha, &h->scal, &h->part, &h->trace_out, &h->xs, &h->Kst, &h->Kss,
-                       &h->pmu, &h->pvar, &h->pkdiag, &h->tblk};
+                       &h->pmu, &h->pvar, &h->pkdiag, &h->tblk, &h->xp};
+    h->xmap_ok = false;
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
     if (h->flags) { cudaFree(h->flags); h->flags = nullptr; }
@@ -917,6 +931,28 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
+// Gram build / gradient trace dispatch: the TMA-staged SEIso kernels (gram_fast.cu) when the kernel program is the single
+// SEIso leaf over all (<= 8) input dimensions, else the generic kernel-program kernels (gram.cu)
+bool use_seiso_fast(gpb200_handle* h, SeIsoFast* sf) {
+    return h->gram_fast && h->prog.fast && h->xmap_ok && h->xp && seiso_fast_prepare(h->prog.par[0], h->prog.par[1], sf);
+}
+cudaError_t launch_gram(gpb200_handle* h, double* G, int64_t ldg, int own_tiles, int nranks, int rank, int own_axis) {
+    SeIsoFast sf;
+    if (use_seiso_fast(h, &sf))
+        return gram_seiso_tma_launch(&h->mapX, h->dxp, sf, h->N, h->Npad, h->noise_var, h->n_noise, h->nugget, G, ldg, h->st,
+                                     own_tiles, nranks, rank, own_axis);
+    return gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, h->n_noise, h->nugget, G, ldg, h->st,
+                             own_tiles, nranks, rank, own_axis);
+}
+cudaError_t launch_trace(gpb200_handle* h, int bm_mod, int bm_rem, int bm_div) {
+    SeIsoFast sf;
+    if (use_seiso_fast(h, &sf))
+        return trace_seiso_tma_launch(&h->mapX, h->dxp, sf, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
+                                      bm_mod, bm_rem, bm_div);
+    return trace_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
+                        bm_mod, bm_rem, bm_div);
+}
+
 #include "shard_impl.cuh"
 
 // collective entry points of a sharded handle: in an in-process group they must be called on the leader (it drives every
@@ -1004,6 +1040,9 @@ void gpb200_destroy(gpb200_handle* h) {
         delete g;
     }
     if (h->st) cudaStreamSynchronize(h->st);
+    if (h->sub) { h->sub->st = nullptr; h->sub->own_stream = false; gpb200_destroy(h->sub); h->sub = nullptr; }
+    if (h->rz) cudaFree(h->rz);
+    if (h->rout) cudaFree(h->rout);
     free_data(h);
     for (auto e : h->evring) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1041,6 +1080,7 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
         h->dist_nb = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "gram_fast")) { h->gram_fast = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "shard")) {                // storage of F / G with several ranks: -1 auto, 0 replicated, 1 row-sharded
         if (value < -1 || value > 1) return fail(h, GPB200_EINVAL, "shard must be -1 (auto), 0 or 1");
         h->shard_opt = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
@@ -1124,6 +1164,16 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
     // x arrives as Julia's d x N column-major (ld = ldx): point i is the contiguous run x[i*ldx .. +d)
     CK(cudaMemcpy2DAsync(h->x, sizeof(double) * d, x, sizeof(double) * ldx, sizeof(double) * d, N,
                          cudaMemcpyHostToDevice, h->st));
+    // second copy with an even row length for the TMA-staged SEIso kernels (row pitch must be a multiple of 16 bytes)
+    h->xmap_ok = false;
+    if (d <= 8) {
+        h->dxp = (d + 1) / 2 * 2;
+        if (!h->xp) CK(cudaMalloc(&h->xp, sizeof(double) * Npad * h->dxp));
+        CK(cudaMemsetAsync(h->xp, 0, sizeof(double) * Npad * h->dxp, h->st));
+        CK(cudaMemcpy2DAsync(h->xp, sizeof(double) * h->dxp, x, sizeof(double) * ldx, sizeof(double) * d, N,
+                             cudaMemcpyHostToDevice, h->st));
+        h->xmap_ok = gemm_make_tensor_map_plain(&h->mapX, h->xp, N, h->dxp, h->dxp, TILE, h->dxp);
+    }
     CK(cudaStreamSynchronize(h->st));
     h->has_data = true;
     h->factored = h->inv_ready = h->alpha_ready = false;
@@ -1221,8 +1271,7 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
         CK(cudaEventRecord(h->ev0, h->st));
         for (auto* q : L) {
             ++q->launches;
-            SCK(q, gram_lower_launch(q->prog, q->x, q->d, q->d, q->N, q->Npad, q->noise_var, n_noise, extra_nugget, q->G, q->ld,
-                                     q->st, q->rb, q->nranks, q->rank, 1));
+            SCK(q, launch_gram(q, q->G, q->ld, q->rb, q->nranks, q->rank, 1));
         }
         CK(cudaEventRecord(h->ev1, h->st));
         { int rc = shard_cholesky(L); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
@@ -1249,13 +1298,12 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
         int rc = dist_alloc(h);
         if (rc) return rc;
         const int NBd = dist_block(h);
-        CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld,
-                             h->st, NBd / TILE, h->nranks, h->rank));
+        CK(launch_gram(h, h->G, h->ld, NBd / TILE, h->nranks, h->rank, 0));
         CK(cudaEventRecord(h->ev1, h->st));
         rc = h->p2p ? cholesky_dist_p2p(h) : cholesky_dist(h);
         if (rc) return rc;
     } else {
-        CK(gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, n_noise, extra_nugget, h->G, h->ld, h->st));
+        CK(launch_gram(h, h->G, h->ld, 0, 1, 0, 0));
         CK(cudaEventRecord(h->ev1, h->st));
         CK(cholesky(h));
     }
@@ -1391,15 +1439,13 @@ int gpb200_grad_kernel(gpb200_handle* h, const double* alpha, double* dmll_kerne
         // fused trace over the own rows of K^-1 (block-cyclic tile rows), P+1 partial sums summed over the ranks
         for (auto* q : Lg) {
             q->launches += 2;
-            SCK(q, trace_launch(q->prog, q->x, q->d, q->d, q->N, q->Npad, q->alpha, q->G, q->ld, q->part, q->trace_out, q->st,
-                                q->nranks, q->rank, q->rb));
+            SCK(q, launch_trace(q, q->nranks, q->rank, q->rb));
         }
         int rc = coll_allreduce_sum(Lg, [&](gpb200_handle* q) { return q->trace_out; }, (size_t)trace_num_acc(h->prog));
         if (rc) { if (Lg[0] != h) h->err = Lg[0]->err; return rc; }
     } else {
     h->launches += 2;
-    CK(trace_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
-                    h->nranks, h->rank));
+    CK(launch_trace(h, h->nranks, h->rank, 1));
     }
     if (!h->sharded && h->nranks > 1) {                    // P+1 partial sums, summed over ranks
         CK(cudaEventRecord(h->ev_x, h->st));
@@ -1473,7 +1519,7 @@ int gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, 
             int rc = shard_predict_solve(Lp, (int)Mpad, Mc, var != nullptr, cov != nullptr);
             if (rc) { if (Lp[0] != h) h->err = Lp[0]->err; return rc; }
             if (var) CK(cudaMemcpyAsync(var + m0, h->pvar, sizeof(double) * Mc, cudaMemcpyDeviceToHost, h->st));
-            if (cov) CK(cudaMemcpy2DAsync(cov, sizeof(double) * M, h->Kss, sizeof(double) * Mpad, sizeof(double) * M, M,
+            if (cov && !h->cov_keep_device) CK(cudaMemcpy2DAsync(cov, sizeof(double) * M, h->Kss, sizeof(double) * Mpad, sizeof(double) * M, M,
                                           cudaMemcpyDeviceToHost, h->st));
         }
         { int rc = sync_all(Lp); if (rc) return rc; }
@@ -1507,8 +1553,9 @@ int gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, 
                 g.C = h->Kss; g.ldc = Mpad; g.M = (int)Mpad; g.N = (int)Mpad; g.K = (int)h->Npad;
                 g.alpha = -1.0; g.beta = 1.0;
                 CK(launch_gemm(h, g));
-                CK(cudaMemcpy2DAsync(cov, sizeof(double) * M, h->Kss, sizeof(double) * Mpad, sizeof(double) * M, M,
-                                     cudaMemcpyDeviceToHost, h->st));
+                if (!h->cov_keep_device)
+                    CK(cudaMemcpy2DAsync(cov, sizeof(double) * M, h->Kss, sizeof(double) * Mpad, sizeof(double) * M, M,
+                                         cudaMemcpyDeviceToHost, h->st));
             }
         }
         CK(cudaStreamSynchronize(h->st));
@@ -1520,6 +1567,67 @@ int gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, 
     return GPB200_OK;
 }
 
+// rand(gp, X, n) (src/GP.jl:120-146): posterior draws  mu* + chol(Sigma* + nugget I) Z  entirely on the device: full predictive
+// covariance (predictMVN), make_posdef!(Sigma; nugget) with the engine's own Cholesky on an M x M sub-engine, unwhiten! as one
+// triangular NT GEMM.  z / samples are Julia's M x nsamp column-major matrices (== nsamp x M row-major).
+int gpb200_rand(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, const double* alpha, int64_t nsamp,
+                const double* z, double nugget, double* mu_minus_mean, double* samples) {
+    if (!h) return GPB200_EINVAL;
+    if (M <= 0 || nsamp <= 0 || !z || !samples || !mu_minus_mean) return fail(h, GPB200_EINVAL, "rand: bad M, nsamp, z, mu or samples");
+    if (!(nugget >= 0.0)) return fail(h, GPB200_EINVAL, "rand: nugget must be >= 0");
+    CK(cudaSetDevice(h->device));
+    static double cov_flag;                                     // non-null marker: the covariance stays in h->Kss
+    h->cov_keep_device = true;
+    int rc = gpb200_predict(h, M, xs, ldxs, alpha, mu_minus_mean, nullptr, &cov_flag);
+    h->cov_keep_device = false;
+    if (rc) return rc;
+    const int64_t Mpad = (M + TILE - 1) / TILE * TILE, Spad = (nsamp + TILE - 1) / TILE * TILE;
+    // sub-engine of size M (shares this handle's stream)
+    if (!h->sub) {
+        rc = gpb200_create(&h->sub, h->device);
+        if (rc) return fail(h, rc, "rand: could not create the M x M sub-engine");
+        cudaStreamDestroy(h->sub->st);
+        h->sub->own_stream = false;
+    }
+    gpb200_handle* sb = h->sub;
+    sb->st = h->st;
+    if (!sb->has_data || sb->N != M) {
+        std::vector<double> dummy((size_t)M, 0.0);
+        rc = gpb200_set_data(sb, M, 1, dummy.data(), 1);
+        if (rc) { h->err = "rand: " + sb->err; return rc; }
+    }
+    ++h->launches;
+    CK(spd_from_cov_launch(sb->G, sb->ld, h->Kss, Mpad, M, Mpad, nugget, h->st));
+    rc = chol_inplace(sb);
+    if (rc) { h->err = "rand: predictive covariance + nugget is not positive definite: " + sb->err; return rc; }
+    // draws: Zt (nsamp x M, zero padded) on the device
+    if (Spad > h->rz_rows || Mpad > h->rz_cols) {
+        if (h->rz) cudaFree(h->rz);
+        if (h->rout) cudaFree(h->rout);
+        h->rz = h->rout = nullptr; h->rz_rows = h->rz_cols = 0;
+        CK(cudaMalloc(&h->rz, sizeof(double) * Spad * Mpad));
+        CK(cudaMalloc(&h->rout, sizeof(double) * Spad * Mpad));
+        h->rz_rows = Spad; h->rz_cols = Mpad;
+    }
+    const int64_t ldz = h->rz_cols;
+    if (h->tma_ok && !gemm_make_tensor_map(&h->mapRz, h->rz, h->rz_rows, ldz, ldz)) return fail(h, GPB200_ECUDA, "rand: tensor map");
+    CK(cudaMemsetAsync(h->rz, 0, sizeof(double) * h->rz_rows * ldz, h->st));
+    CK(cudaMemcpy2DAsync(h->rz, sizeof(double) * ldz, z, sizeof(double) * M, sizeof(double) * M, nsamp, cudaMemcpyHostToDevice, h->st));
+    {   // out[s, m] = sum_{k <= m} Zt[s, k] L[m, k]       (unwhiten!: L Z)
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{GemmBuf{h->tma_ok ? &h->mapRz : nullptr, h->rz, ldz}, bufNone(), 0, 0};
+        g.B = GemmOperand{bufF(sb), bufNone(), 0, 0};
+        g.C = h->rout; g.ldc = ldz; g.M = (int)Spad; g.N = (int)Mpad; g.K = (int)Mpad;
+        g.flags = GEMM_KHI_N;
+        CK(launch_gemm(h, g));
+    }
+    ++h->launches;
+    CK(add_rowvec_launch(h->rout, ldz, h->pmu, nsamp, M, h->st));                          // + mu (K*' alpha part)
+    CK(cudaMemcpy2DAsync(samples, sizeof(double) * M, h->rout, sizeof(double) * ldz, sizeof(double) * M, nsamp, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return GPB200_OK;
+}
+
 int gpb200_get_gram(gpb200_handle* h, double* K) {
     if (!h || !K) return GPB200_EINVAL;
     if (!h->has_data || !h->has_kernel) return fail(h, GPB200_ESTATE, "get_gram: set_data and set_kernel first");
@@ -1527,8 +1635,7 @@ int gpb200_get_gram(gpb200_handle* h, double* K) {
     double* tmp = nullptr;
     const size_t nn = sizeof(double) * (size_t)h->Npad * (size_t)h->Npad;
     CK(cudaMalloc(&tmp, nn));
-    cudaError_t e = gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, h->n_noise, h->nugget,
-                                      tmp, h->Npad, h->st);
+    cudaError_t e = launch_gram(h, tmp, h->Npad, 0, 1, 0, 0);
     if (e == cudaSuccess)
         e = cudaMemcpy2DAsync(K, sizeof(double) * h->N, tmp, sizeof(double) * h->Npad, sizeof(double) * h->N, h->N,
                               cudaMemcpyDeviceToHost, h->st);

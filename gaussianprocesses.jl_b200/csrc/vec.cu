@@ -456,3 +456,31 @@ cudaError_t exp2x_launch(const double* ln, int64_t n, double* out, cudaStream_t 
     exp2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ln, n, out);
     return cudaGetLastError();
 }
+
+// ---- posterior sampling helpers (gpb200_rand) -------------------------------------------------------------------
+namespace {
+// lower tiles of dst (n_pad x n_pad, ld ldd) = src[:n, :n] + nugget I ; identity in the padding
+__global__ void spd_from_cov_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src, long long lds,
+                                    long long n, long long npad, double nugget) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= npad || (j >> 7) > (i >> 7)) return;
+    double v;
+    if (i < n && j < n) v = src[i * lds + j] + (i == j ? nugget : 0.0);
+    else v = (i == j) ? 1.0 : 0.0;
+    dst[i * ldd + j] = v;
+}
+__global__ void add_rowvec_kernel(double* __restrict__ A, long long ld, const double* __restrict__ v, long long nrows, long long ncols) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j < ncols && i < nrows) A[i * ld + j] += v[j];
+}
+}  // namespace
+cudaError_t spd_from_cov_launch(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int64_t npad, double nugget, cudaStream_t st) {
+    dim3 grid((unsigned)((npad + 255) / 256), (unsigned)npad);
+    spd_from_cov_kernel<<<grid, 256, 0, st>>>(dst, ldd, src, lds, n, npad, nugget);
+    return cudaGetLastError();
+}
+cudaError_t add_rowvec_launch(double* A, int64_t ld, const double* v, int64_t nrows, int64_t ncols, cudaStream_t st) {
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)nrows);
+    add_rowvec_kernel<<<grid, 256, 0, st>>>(A, ld, v, nrows, ncols);
+    return cudaGetLastError();
+}

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "gpb200_grad_prepare": (C.c_int, [_H]),
     "gpb200_grad_kernel": (C.c_int, [_H, _dp, _dp, _dp]),
     "gpb200_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp]),
+    "gpb200_rand": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp, C.c_double, _dp, _dp]),
     "gpb200_get_gram": (C.c_int, [_H, _dp]),
     "gpb200_get_factor": (C.c_int, [_H, _dp]),
     "gpb200_get_inverse": (C.c_int, [_H, _dp]),
@@ -213,6 +214,20 @@ class Engine:
                                              _as_dp(var) if want_var else None,
                                              _as_dp(cov) if full_cov else None), "predict")
         return mu, var, cov
+
+    def rand(self, xs_pm, z, nugget=1e-10, alpha=None):
+        """z: (nsamp, M) standard-normal draws (== Julia's M x nsamp column-major).  Returns (mu_minus_mean[M], samples (nsamp, M))."""
+        xs_pm = np.ascontiguousarray(xs_pm, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        M, d = xs_pm.shape
+        if d != self.d or z.ndim != 2 or z.shape[1] != M:
+            raise ValueError("rand: inconsistent dimensions")
+        mu = np.empty(M)
+        out = np.empty_like(z)
+        ap = _as_dp(np.ascontiguousarray(alpha, dtype=np.float64)) if alpha is not None else None
+        self._check(self._lib.gpb200_rand(self._h, M, _as_dp(xs_pm), d, ap, z.shape[0], _as_dp(z), float(nugget), _as_dp(mu),
+                                          _as_dp(out)), "rand")
+        return mu, out
 
     # -- debug ----------------------------------------------------------------------------
     def gram(self):
@@ -452,6 +467,9 @@ class LocalGroupEngine:
 
     def predict(self, *a, **k):
         return self.lead.predict(*a, **k)
+
+    def rand(self, *a, **k):
+        return self.lead.rand(*a, **k)
 
     def timings(self):
         return self.lead.timings()

@@ -200,14 +200,17 @@ class GPE:
         return float(np.sum(-0.5 * np.log(2.0 * np.pi * s2) - 0.5 * (self.y - mu) ** 2 / s2))
 
     def rand(self, x, n=1, nugget=1e-10, rng=None):
-        """rand(gp, X, n) (src/GP.jl:120-146): n posterior draws at the columns of x.  The M x M predictive
-        covariance comes from the device (predict_f full_cov), its small Cholesky and the normal draws stay
-        on the host exactly like the reference's make_posdef! + unwhiten!."""
+        """rand(gp, X, n) (src/GP.jl:120-146): n posterior draws at the columns of x, computed on the device (predictive
+        covariance, make_posdef!(Σ; nugget) Cholesky, unwhiten!); only the standard-normal draws come from the host RNG,
+        like the reference's randn(nobs, n_sample).  Returns a (npred, n) array."""
         rng = np.random.default_rng() if rng is None else rng
-        mu, Sigma = self.predict_f(x, full_cov=True)
-        Sigma = Sigma + nugget * np.eye(Sigma.shape[0])                  # make_posdef!(Σraw; nugget)
-        L = np.linalg.cholesky(Sigma)
-        return mu[:, None] + L @ rng.standard_normal((mu.size, int(n)))
+        x = _as_dxn(x)
+        if x.shape[0] != self.dim:
+            raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
+        xs = np.ascontiguousarray(x.T)
+        z = rng.standard_normal((int(n), xs.shape[0]))
+        _, draws = self._eng.rand(xs, z, nugget=nugget)
+        return (draws + self.mean.mean(xs)[None, :]).T
 
     # ---- parameters ----------------------------------------------------------------------
     def get_params(self, noise=True, domean=True, kern=True):      # GPE.jl:447-458

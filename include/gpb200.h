@@ -123,6 +123,13 @@ int  gpb200_grad_kernel(gpb200_handle* h, const double* alpha, double* dmll_kern
 int  gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs,
                     const double* alpha, double* mu_minus_mean, double* var, double* cov);
 
+/* rand(gp, X, n) (src/GP.jl:120-146): n posterior draws at the M test points, on the device: predictMVN's full covariance,
+ * make_posdef!(Sigma; nugget) (Cholesky of the M x M matrix), unwhiten!(Sigma, Z) and + mu.  z and samples are M x nsamp
+ * column-major (Julia `randn(M, n)` / the returned matrix); mu_minus_mean[M] as in gpb200_predict (the shim adds mean(x*) to
+ * it and to every draw).  Returns k > 0 if Sigma + nugget I is not positive definite (PosDefException).               */
+int  gpb200_rand(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, const double* alpha, int64_t nsamp,
+                 const double* z, double nugget, double* mu_minus_mean, double* samples);
+
 /* ---- debug / introspection (Base.Matrix(::P), mat(::P), tests) ----------------------------- */
 int  gpb200_get_gram(gpb200_handle* h, double* K);        /* N x N, K_y rebuilt from x, theta   */
 int  gpb200_get_factor(gpb200_handle* h, double* U);      /* N x N column-major upper U, K_y=U'U */
@@ -146,6 +153,8 @@ int64_t gpb200_launch_count(gpb200_handle* h);
  *   "profile"    1 = CUDA events around every GEMM launch (see gpb200_get_timings)
  *   "dist_nb"    multi-GPU: width of an owned block column, 0 = auto (~N/(8*ranks))
  *   "p2p"        multi-GPU: 1 = fused panel push over peer memory (after gpb200_ipc_import), 0 = NCCL broadcast
+ *   "gram_fast"  1 (default) = TMA-staged SEIso Gram / trace kernels (gram_fast.cu) when the kernel is one SEIso leaf over
+ *                <= 8 dimensions, 0 = always the generic kernel-program kernels (cross-check)
  *   "shard"      multi-GPU storage of the two N x N buffers: 1 = row-sharded (each rank maps only its own block rows),
  *                0 = replicated, -1 (default) = sharded only when the replicated form would not fit the device
  *   "shard_rb"   row-sharded ownership block in 128-row tiles (panel width 128*rb): 0 auto, 1, 2, 4, 8

@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, call 3 (1 GPU): TMA-staged SEIso Gram/trace kernels + device rand: parity, timing, ncu; sharded groups again
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_shard.py tests/test_gpu_fullsize.py tests/test_gpu_fitc.py -q -m gpu -s --durations=8 > gpurun_out/r02_pytest_3.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02_pytest_3.log
+grep -E "passed|failed|^E  |Error" gpurun_out/r02_pytest_3.log | head -30
+timeout 600 python profiles/tools/probe_gram.py 32768 > gpurun_out/r02_probe_gram.txt 2>&1; cat gpurun_out/r02_probe_gram.txt
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_3.json 2> gpurun_out/r02_bench_3.err; echo "bench exit $?" >> gpurun_out/r02_bench_3.err
+cut -c1-900 gpurun_out/r02_bench_3.json
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:gram_seiso|trace_seiso" -c 2 -o gpurun_out/r02_prof_gram_fast -f python profiles/tools/probe_gram.py 32768 > gpurun_out/r02_ncu_gram.log 2>&1
+ncu -i gpurun_out/r02_prof_gram_fast.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active > gpurun_out/r02_ncu_gram_metrics.csv 2>&1
+cat gpurun_out/r02_ncu_gram_metrics.csv | cut -c1-1500

@@ -288,3 +288,62 @@ def test_predict_chunking_and_explicit_alpha(engine, monkeypatch):
     monkeypatch.delenv("GPB200_PREDICT_CHUNK")
     mu1, var1, _ = engine.predict(Xs)                              # single chunk, resident alpha
     assert np.allclose(mu1, mu, rtol=0, atol=1e-12 * np.max(np.abs(mu))) and np.allclose(var1, var, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("d,N,ll,ls", [(1, 300, 0.2, 0.1), (2, 515, -0.5, 0.3), (5, 700, 0.4, -0.2), (8, 1300, 0.3, 0.3),
+                                       (8, 640, -2.5, 0.0), (3, 500, 0.0, 9.0), (4, 500, 0.5, -9.0)])
+def test_seiso_tma_kernels_match_generic_and_oracle(engine, d, N, ll, ls):
+    """gram_fast.cu (TMA-staged tiles, table-based exp2) against the generic kernel-program kernels (libm exp) and the
+    oracle: Gram entries to 4 ulp of the largest entry, incl. the deep-underflow region (ll = -2.5: exp(-r/2l^2) down to
+    1e-300), extreme signal variances, padding tiles and per-point noise; gradient trace to 1e-12."""
+    import gpb200
+    X, y, _ = make_data(N, d, 31 + d)
+    if ll < -2:
+        X *= 4.0                                           # push exp arguments below -700
+    k = gpb200.SEIso(ll, ls)
+    noise = -0.3 + 0.1 * np.cos(np.arange(N))              # VectorParam noise (src/GPE.jl:177-186)
+    theta, _ = _setup(engine, k, X, nb=0, gemm=0)
+    res = {}
+    for fast in (1, 0):
+        engine.set_option("gram_fast", fast)
+        engine.factorize(theta, noise)
+        K = engine.gram()
+        alpha, mll = engine.mll(y)
+        engine.grad_prepare()
+        g, trA = engine.grad_kernel()
+        res[fast] = (K, mll, g, trA)
+    engine.set_option("gram_fast", 1)
+    Ko = orc.cov(k.spec(), X) + np.diag(np.exp(2 * noise))
+    scale = np.max(np.abs(Ko))
+    assert np.max(np.abs(res[1][0] - Ko)) <= 1e-15 * scale * 4
+    assert np.max(np.abs(res[1][0] - res[0][0])) <= 1e-15 * scale * 4
+    # relative accuracy of the small entries too (not only in the max norm): compare where the oracle is > 1e-280
+    big = Ko > 1e-280 * np.exp(2 * ls)
+    rel = np.abs(res[1][0][big] - Ko[big]) / Ko[big]
+    assert np.max(rel) <= 1e-12, np.max(rel)               # |x| * (rounding of r) amplification in the exponent, |x| <= 645
+    assert abs(res[1][1] - res[0][1]) <= 1e-12 * abs(res[0][1])
+    assert np.allclose(res[1][2], res[0][2], rtol=1e-10, atol=1e-12 * np.max(np.abs(res[0][2])))
+    assert abs(res[1][3] - res[0][3]) <= 1e-10 * abs(res[0][3])
+
+
+@pytest.mark.parametrize("M,n", [(37, 5), (300, 130)])
+def test_rand_on_device_matches_oracle(engine, M, n):
+    """rand(gp, X, n) (src/GP.jl:120-146) on the device: with the SAME standard-normal draws the samples equal
+    mu* + chol(Sigma* + nugget I) Z of the oracle's predictMVN (full covariance)."""
+    import gpb200
+    X, y, _ = make_data(900, 3, 5)
+    Xs = np.random.default_rng(8).standard_normal((M, 3)) * 1.5
+    k = gpb200.Mat52Iso(0.2, 0.1) + gpb200.SEIso(0.5, -0.5)
+    theta, _ = _setup(engine, k, X, nb=0, gemm=0)
+    engine.factorize(theta, -1.0)
+    engine.mll(y)
+    o = orc.fit(k.spec(), X, y, -1.0)
+    mo, co = orc.predict_f(k.spec(), X, o, Xs, full_cov=True)
+    z = np.random.default_rng(9).standard_normal((n, M))
+    mu, draws = engine.rand(Xs, z, nugget=1e-6)
+    L = np.linalg.cholesky(co + 1e-6 * np.eye(M))
+    want = mo[None, :] + z @ L.T
+    assert _rel(mu, mo) < RTOL
+    assert np.max(np.abs(draws - want)) <= 1e-8 * np.max(np.abs(want))
+    with pytest.raises(ValueError):
+        engine.rand(Xs, z[:, :-1])
