@@ -260,6 +260,8 @@ def main():
         # Cholesky with NCCL panel broadcasts, split inverse, row-cyclic W'W + trace)
         with StdoutToStderr():
             gp.init_distributed()
+    if os.environ.get("GPB200_SHARD") is not None:          # storage-mode override (replicated 0 / row-sharded 1) for A/B runs
+        eng.set_option("shard", int(os.environ["GPB200_SHARD"]))
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     theta = np.array([LL, LSIG])
@@ -412,7 +414,7 @@ def main():
                        "parallelism": "1 GPU" if world == 1 else
                        "%d GPUs: 1-D block-cyclic block columns (NCCL panel broadcast over NVLink, look-ahead), "
                        "split level-parallel inverse + all-gather, tile-row-cyclic W'W/trace + all-reduce of P+1 sums; "
-                       "F/G replicated per GPU" % world,
+                       "F/G %s" % (world, "row-sharded over the GPUs (own block rows mapped)" if eng.storage_info()["sharded"] else "replicated per GPU"),
                        "phases_ms": {k: round(v, 3) for k, v in tmr.items() if k in ("gram", "cholesky", "solve_mll", "inverse", "trace")},
                        "predict_f_ms_M4096": predict_ms},
             "clocks": clocks,

@@ -140,12 +140,13 @@ struct gpb200_handle {
     int shard_rb_opt = 0;                      // option "shard_rb": ownership block in 128-row tiles (0 = auto)
     bool sharded = false;                      // current storage mode of F / G
     int rb = 4;                                // effective ownership block (tiles); panel width NBp = 128 * rb
+    int shard_la = 1;                          // option "shard_la": look-ahead schedules of the sharded Cholesky / inverse
     int row_lim = 0;                           // chol_panel: rows below this limit only (diagonal block of a sharded panel); 0 = Npad
     VmBuf vmF, vmG;
-    double* P[2] = {nullptr, nullptr};         // panel buffers, Npad x NBp (global row order); P[1] doubles as the NBp x Npad row panel
+    double* P[4] = {nullptr, nullptr, nullptr, nullptr};   // panel buffers, Npad x NBp (global row order); P[1], P[3] double as NBp x Npad row panels
     double* Sbuf = nullptr;                    // all-gather staging: nranks regions of S_per_rank doubles; scratch of the inverse sweep
     size_t S_per_rank = 0;
-    CUtensorMap mapP[2] = {}, mapXR{}, mapS{};
+    CUtensorMap mapP[4] = {}, mapXR[2] = {}, mapS{};
     double* red = nullptr;                     // small reduction scratch (local group all-reduce)
     int* redi = nullptr;
     struct gpb200_group* grp = nullptr;        // in-process group of virtual ranks on one device (gpb200_group_create)
@@ -1085,6 +1086,7 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
         if (value < -1 || value > 1) return fail(h, GPB200_EINVAL, "shard must be -1 (auto), 0 or 1");
         h->shard_opt = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
+    if (!strcmp(key, "shard_la")) { h->shard_la = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "shard_rb")) {             // ownership block of the row-sharded storage in 128-row tiles (panel = 128 * rb)
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(h, GPB200_EINVAL, "shard_rb must be 0 (auto), 1, 2, 4 or 8");
         h->shard_rb_opt = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
@@ -1274,7 +1276,7 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
             SCK(q, launch_gram(q, q->G, q->ld, q->rb, q->nranks, q->rank, 1));
         }
         CK(cudaEventRecord(h->ev1, h->st));
-        { int rc = shard_cholesky(L); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
+        { int rc = h->shard_la ? shard_cholesky_la(L) : shard_cholesky(L); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
         CK(cudaEventRecord(h->ev2, h->st));
         int info_s = 0;
         CK(cudaMemcpyAsync(&info_s, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -1403,7 +1405,7 @@ int gpb200_grad_prepare(gpb200_handle* h) {
     if (h->sharded) {
         Locals L;
         { int rc = shard_entry(h, L); if (rc) return rc; }
-        { int rc = shard_inverse(L); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
+        { int rc = h->shard_la ? shard_inverse_la(L) : shard_inverse(L); if (rc) { if (L[0] != h) h->err = L[0]->err; return rc; } }
         CK(cudaEventRecord(h->ev1, h->st));
         { int rc = sync_all(L); if (rc) return rc; }
         for (auto* q : L) { profile_collect(q); q->inv_ready = true; }

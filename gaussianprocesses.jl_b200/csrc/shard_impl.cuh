@@ -293,7 +293,7 @@ int shard_pick_rb(gpb200_handle* h) {
 }
 
 void shard_free_buffers(gpb200_handle* h) {
-    for (int i = 0; i < 2; ++i) { if (h->P[i]) cudaFree(h->P[i]); h->P[i] = nullptr; }
+    for (int i = 0; i < 4; ++i) { if (h->P[i]) cudaFree(h->P[i]); h->P[i] = nullptr; }
     if (h->Sbuf) cudaFree(h->Sbuf);
     if (h->red) cudaFree(h->red);
     if (h->redi) cudaFree(h->redi);
@@ -347,7 +347,7 @@ int alloc_FG_sharded(gpb200_handle* h) {
     h->G = (double*)h->vmG.base;
     const size_t nbp = (size_t)shard_panel_width(h);
     const size_t pelems = Np * nbp;
-    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&h->P[i], sizeof(double) * pelems));
+    for (int i = 0; i < 4; ++i) CK(cudaMalloc(&h->P[i], sizeof(double) * pelems));
     // all-gather staging: every rank's rows below a panel, padded to the largest per-rank count
     const size_t max_own_tiles = (size_t)shard_own_before(tiles, 0, h->rb, h->nranks);      // rank 0 owns the most
     h->S_per_rank = max_own_tiles * TILE * nbp;
@@ -358,7 +358,10 @@ int alloc_FG_sharded(gpb200_handle* h) {
     h->tma_ok = make_FG_maps(h) &&
                 gemm_make_tensor_map(&h->mapP[0], h->P[0], Np, nbp, nbp) &&
                 gemm_make_tensor_map(&h->mapP[1], h->P[1], Np, nbp, nbp) &&
-                gemm_make_tensor_map(&h->mapXR, h->P[1], nbp, Np, Np) &&
+                gemm_make_tensor_map(&h->mapP[2], h->P[2], Np, nbp, nbp) &&
+                gemm_make_tensor_map(&h->mapP[3], h->P[3], Np, nbp, nbp) &&
+                gemm_make_tensor_map(&h->mapXR[0], h->P[1], nbp, Np, Np) &&
+                gemm_make_tensor_map(&h->mapXR[1], h->P[3], nbp, Np, Np) &&
                 gemm_make_tensor_map(&h->mapS, h->Sbuf, Np, nbp, nbp);
     // without TMA descriptors the GEMMs fall back to the plain-load kernel (launch_gemm), storage_info reports it
     return GPB200_OK;
@@ -387,7 +390,7 @@ int ensure_storage(gpb200_handle* h) {
 }
 
 GemmBuf bufP(gpb200_handle* h, int i) { return GemmBuf{&h->mapP[i], h->P[i], (int64_t)shard_panel_width(h)}; }
-GemmBuf bufXR(gpb200_handle* h) { return GemmBuf{&h->mapXR, h->P[1], h->Npad}; }
+GemmBuf bufXR(gpb200_handle* h, int set = 0) { return GemmBuf{&h->mapXR[set], h->P[2 * set + 1], h->Npad}; }
 GemmBuf bufS(gpb200_handle* h) { return GemmBuf{&h->mapS, h->Sbuf, (int64_t)shard_panel_width(h)}; }
 
 void own_rows_filter(gpb200_handle* h, GemmDesc& g, int row0) {
@@ -399,7 +402,7 @@ void own_cols_filter(gpb200_handle* h, GemmDesc& g, int row0_of_B) {
 
 // ---- Cholesky -------------------------------------------------------------------------------------------------
 // G[r1.., c0+off .. c0+off+n) <- (same) * L_kk[off.., off..]^-T  on this rank's rows >= r1 (L_kk sits in P[0] rows c0..)
-cudaError_t shard_trsm_rows(gpb200_handle* h, int c0, int r1, int off, int n) {
+cudaError_t shard_trsm_rows(gpb200_handle* h, int c0, int r1, int off, int n, int pb = 0) {
     const int rows = (int)h->Npad - r1;
     if (n == TILE) {
         GemmDesc g = gemm_desc_default();
@@ -414,18 +417,18 @@ cudaError_t shard_trsm_rows(gpb200_handle* h, int c0, int r1, int off, int n) {
     while (n1 * 2 < n) n1 *= 2;
     const int n2 = n - n1;
     cudaError_t e;
-    if ((e = shard_trsm_rows(h, c0, r1, off, n1)) != cudaSuccess) return e;
+    if ((e = shard_trsm_rows(h, c0, r1, off, n1, pb)) != cudaSuccess) return e;
     {
         GemmDesc g = gemm_desc_default();
         g.A = GemmOperand{bufG(h), bufNone(), r1, c0 + off};
-        g.B = GemmOperand{bufP(h, 0), bufNone(), c0 + off + n1, off};                  // L21 of the diagonal block
+        g.B = GemmOperand{bufP(h, pb), bufNone(), c0 + off + n1, off};                 // L21 of the diagonal block
         g.C = h->G; g.ldc = h->ld; g.c_row0 = r1; g.c_col0 = c0 + off + n1;
         g.M = rows; g.N = n2; g.K = n1;
         g.alpha = -1.0; g.beta = 1.0;
         own_rows_filter(h, g, r1);
         if ((e = launch_gemm(h, g)) != cudaSuccess) return e;
     }
-    return shard_trsm_rows(h, c0, r1, off + n1, n2);
+    return shard_trsm_rows(h, c0, r1, off + n1, n2, pb);
 }
 
 int shard_cholesky(const Locals& L) {
@@ -486,6 +489,117 @@ int shard_cholesky(const Locals& L) {
             g.flags = GEMM_LOWER_ONLY;
             own_rows_filter(q, g, r1);
             SCK(q, launch_gemm(q, g));
+        }
+    }
+    return coll_allreduce_min_info(L);
+}
+
+// Same factorisation with LOOK-AHEAD: the latency-bound chain of a panel (diagonal-block factorisation, its broadcast, the
+// R-way split TRSM, the all-gather) runs on the high-priority side stream while the main stream applies the PREVIOUS panel
+// to the bulk of the trailing matrix.  Per panel the main stream first updates only the columns of the next block ("narrow"
+// update, K = NBp, a few hundred tiles), hands over to the chain, then does the rest.  Panel buffers alternate (P[k & 1]).
+int shard_cholesky_la(const Locals& L) {
+    gpb200_handle* h0 = L[0];
+    const int Np = (int)h0->Npad, R = h0->nranks, NBp = shard_panel_width(h0);
+    const int nblk = (Np + NBp - 1) / NBp;
+    const long long tiles = Np / TILE;
+    for (auto* q : L) {
+        if (!q->st_side) return fail(q, GPB200_ECUDA, "sharded look-ahead needs the side stream");
+        cudaEvent_t e = ring_event(q);                       // the chain starts after the Gram build
+        SCK(q, cudaEventRecord(e, q->st));
+        SCK(q, cudaStreamWaitEvent(q->st_side, e, 0));
+    }
+    std::vector<cudaEvent_t> ev_panel(L.size());
+    for (int k = 0; k < nblk; ++k) {
+        const int c0 = k * NBp, nb = std::min(NBp, Np - c0), o = k % R, r1 = c0 + nb, pb = k & 1;
+        const int t1 = r1 / TILE;
+        // ---------------- chain of panel k, on the side streams ----------------
+        for (auto* q : L) std::swap(q->st, q->st_side);
+        int rc = GPB200_OK;
+        do {
+            for (auto* q : L) {
+                if (q->rank != o) continue;
+                const int la = q->lookahead;
+                q->lookahead = 0; q->row_lim = r1;
+                cudaError_t e = chol_panel(q, c0, nb, NBp);
+                q->row_lim = 0; q->lookahead = la;
+                if (e != cudaSuccess) { q->err = std::string("chol_panel: ") + cudaGetErrorString(e); rc = GPB200_ECUDA; break; }
+                ++q->launches;
+                e = shard_copy_lower(q->P[pb] + (size_t)c0 * NBp, NBp, q->F + (size_t)c0 * q->ld + c0, q->ld, nb, q->st);
+                if (e != cudaSuccess) { q->err = cudaGetErrorString(e); rc = GPB200_ECUDA; break; }
+            }
+            if (rc) break;
+            if ((rc = coll_group_begin(L))) break;
+            if ((rc = coll_bcast(L, o, [&](gpb200_handle* q) { return (void*)(q->P[pb] + (size_t)c0 * NBp); }, sizeof(double) * (size_t)nb * NBp))) break;
+            if ((rc = coll_bcast(L, o, [&](gpb200_handle* q) { return (void*)(q->Dinv + (size_t)c0 * TILE); }, sizeof(double) * (size_t)nb * TILE))) break;
+            if ((rc = coll_bcast(L, o, [&](gpb200_handle* q) { return (void*)(q->DinvT + (size_t)c0 * TILE); }, sizeof(double) * (size_t)nb * TILE))) break;
+            if ((rc = coll_bcast(L, o, [&](gpb200_handle* q) { return (void*)(q->logd + c0); }, sizeof(double) * (size_t)nb))) break;
+            if ((rc = coll_group_end(L))) break;
+            if (r1 >= Np) break;
+            long long maxown = 0;
+            for (int q = 0; q < R; ++q)
+                maxown = std::max(maxown, shard_own_before(tiles, q, h0->rb, R) - shard_own_before(t1, q, h0->rb, R));
+            const size_t per = (size_t)maxown * TILE * NBp;
+            for (auto* q : L) {
+                cudaError_t e = shard_trsm_rows(q, c0, r1, 0, nb, pb);
+                ++q->launches;
+                if (e == cudaSuccess) e = shard_scatter_rows(q->G, q->F, q->ld, Np, c0, nb, t1, q->Sbuf + (size_t)q->rank * per, NBp, own_of(q), q->st);
+                if (e != cudaSuccess) { q->err = cudaGetErrorString(e); rc = GPB200_ECUDA; break; }
+            }
+            if (rc) break;
+            if ((rc = coll_allgather(L, [&](gpb200_handle* q) { return (void*)q->Sbuf; }, sizeof(double) * per))) break;
+            for (auto* q : L) {
+                ++q->launches;
+                cudaError_t e = shard_unpack_panel(q->P[pb], NBp, Np, nb, t1, q->Sbuf, (int64_t)per, own_of(q), q->st);
+                if (e == cudaSuccess && q->rank == o) {
+                    ++q->launches;
+                    e = shard_transpose(q->F + (size_t)c0 * q->ld + r1, q->ld, q->P[pb] + (size_t)r1 * NBp, NBp, Np - r1, nb, q->st);
+                }
+                if (e != cudaSuccess) { q->err = cudaGetErrorString(e); rc = GPB200_ECUDA; break; }
+            }
+        } while (false);
+        if (!rc) {
+            for (size_t i = 0; i < L.size(); ++i) {
+                ev_panel[i] = ring_event(L[i]);
+                if (cudaEventRecord(ev_panel[i], L[i]->st) != cudaSuccess) { L[i]->err = "cudaEventRecord failed"; rc = GPB200_ECUDA; }
+            }
+        }
+        for (auto* q : L) std::swap(q->st, q->st_side);           // back to the main streams
+        if (rc) { if (L[0]->err.empty()) for (auto* q : L) if (!q->err.empty()) { L[0]->err = q->err; break; } return rc; }
+        if (r1 >= Np) {
+            for (size_t i = 0; i < L.size(); ++i) SCK(L[i], cudaStreamWaitEvent(L[i]->st, ev_panel[i], 0));
+            break;
+        }
+        // ---------------- main streams: apply panel k ----------------
+        const int nb1 = std::min(NBp, Np - r1), r2 = r1 + nb1;
+        for (size_t i = 0; i < L.size(); ++i) {
+            gpb200_handle* q = L[i];
+            SCK(q, cudaStreamWaitEvent(q->st, ev_panel[i], 0));
+            {   // narrow: the columns of the next block, own rows >= r1 (lower trapezoid)
+                GemmDesc g = gemm_desc_default();
+                g.A = GemmOperand{bufP(q, pb), bufNone(), r1, 0};
+                g.B = GemmOperand{bufP(q, pb), bufNone(), r1, 0};
+                g.C = q->G; g.ldc = q->ld; g.c_row0 = r1; g.c_col0 = r1;
+                g.M = Np - r1; g.N = nb1; g.K = nb;
+                g.alpha = -1.0; g.beta = 1.0;
+                g.flags = GEMM_LOWER_ONLY;
+                own_rows_filter(q, g, r1);
+                SCK(q, launch_gemm(q, g));
+            }
+            cudaEvent_t e = ring_event(q);
+            SCK(q, cudaEventRecord(e, q->st));
+            SCK(q, cudaStreamWaitEvent(q->st_side, e, 0));           // the chain of panel k+1 may start
+            if (r2 < Np) {   // the rest of the trailing matrix
+                GemmDesc g = gemm_desc_default();
+                g.A = GemmOperand{bufP(q, pb), bufNone(), r2, 0};
+                g.B = GemmOperand{bufP(q, pb), bufNone(), r2, 0};
+                g.C = q->G; g.ldc = q->ld; g.c_row0 = r2; g.c_col0 = r2;
+                g.M = Np - r2; g.N = Np - r2; g.K = nb;
+                g.alpha = -1.0; g.beta = 1.0;
+                g.flags = GEMM_LOWER_ONLY;
+                own_rows_filter(q, g, r2);
+                SCK(q, launch_gemm(q, g));
+            }
         }
     }
     return coll_allreduce_min_info(L);
@@ -605,6 +719,128 @@ int shard_inverse(const Locals& L) {
                 own_rows_filter(q, g, j0);
                 SCK(q, launch_gemm(q, g));
             }
+        }
+    }
+    return GPB200_OK;
+}
+
+// The same sweep with LOOK-AHEAD.  Chain of panel J (side stream): finalise X_J, broadcast, transpose, and the part of the
+// TRTRI update that the NEXT finalisation needs (rows of block J-1 only); main stream: the bulk TRTRI update (rows before
+// block J-1) and the LAUUM part of panel J.  Panel buffers alternate between two sets {P[2s], P[2s+1]}.  Dependencies:
+//   chain(K) starts after main(K+2) finished (its accumulators received panel K+2's contribution; buffer set K&1 is free),
+//   its narrow update waits for main(K+1)'s TRTRI part (both add into the rows of block K-1), main(K) waits for chain(K).
+int shard_inverse_la(const Locals& L) {
+    gpb200_handle* h0 = L[0];
+    const int Np = (int)h0->Npad, R = h0->nranks, NBp = shard_panel_width(h0);
+    const int nblk = (Np + NBp - 1) / NBp;
+    const size_t nl = L.size();
+    for (auto* q : L) {
+        if (!q->st_side) return fail(q, GPB200_ECUDA, "sharded look-ahead needs the side stream");
+        for (auto& run : q->vmG.runs) SCK(q, cudaMemsetAsync((char*)q->G + run.first, 0, run.second, q->st));
+        for (int k = q->rank; k < nblk; k += R) {
+            const int c0 = k * NBp, nb = std::min(NBp, Np - c0);
+            for (int s = TILE; s < nb; s *= 2) {
+                const int batch = (nb + 2 * s - 1) / (2 * s);
+                const int n2 = (nb - s < s) ? nb - s : s;
+                SCK(q, merge_inverse(q, c0, s, n2, batch));
+            }
+        }
+        cudaEvent_t e = ring_event(q);
+        SCK(q, cudaEventRecord(e, q->st));
+        SCK(q, cudaStreamWaitEvent(q->st_side, e, 0));
+    }
+    // per local rank: events of the two previous main steps
+    std::vector<cudaEvent_t> ev_full1(nl, nullptr), ev_full2(nl, nullptr), ev_trtri1(nl, nullptr), ev_panel(nl, nullptr);
+    for (int k = nblk - 1; k >= 0; --k) {
+        const int j0 = k * NBp, nb = std::min(NBp, Np - j0), o = k % R, r1 = j0 + nb;
+        const int ncols = Np - r1, set = k & 1;
+        const int j0p = (k > 0) ? (k - 1) * NBp : 0;                 // start of block k-1 (size NBp)
+        // ---------------- chain of panel k ----------------
+        for (size_t i = 0; i < nl; ++i) {
+            gpb200_handle* q = L[i];
+            if (ev_full2[i]) SCK(q, cudaStreamWaitEvent(q->st_side, ev_full2[i], 0));       // main(k+2) done
+            std::swap(q->st, q->st_side);
+        }
+        int rc = GPB200_OK;
+        do {
+            for (auto* q : L) {
+                if (q->rank != o) continue;
+                cudaError_t e = cudaSuccess;
+                if (ncols > 0) {
+                    ++q->launches;
+                    e = shard_transpose(q->Sbuf + (size_t)r1 * NBp, NBp, q->G + (size_t)j0 * q->ld + r1, q->ld, nb, ncols, q->st);
+                    GemmDesc g = gemm_desc_default();
+                    g.A = GemmOperand{bufS(q), bufNone(), r1, 0};
+                    g.B = GemmOperand{bufG(q), bufDinvT(q), j0, j0};
+                    g.C = q->P[2 * set]; g.ldc = NBp; g.c_row0 = r1; g.c_col0 = 0;
+                    g.Ct = q->G; g.ldct = q->ld; g.ct_row0 = j0; g.ct_col0 = r1;
+                    g.M = ncols; g.N = nb; g.K = nb;
+                    g.alpha = -1.0;
+                    g.flags = GEMM_KLO_N;
+                    if (e == cudaSuccess) e = launch_gemm(q, g);
+                }
+                ++q->launches;
+                if (e == cudaSuccess) e = shard_pack_wblock(q->P[2 * set], NBp, q->G, q->ld, q->Dinv, j0, nb, q->st);
+                if (e != cudaSuccess) { q->err = cudaGetErrorString(e); rc = GPB200_ECUDA; break; }
+            }
+            if (rc) break;
+            if ((rc = coll_bcast(L, o, [&](gpb200_handle* q) { return (void*)(q->P[2 * set] + (size_t)j0 * NBp); },
+                                 sizeof(double) * (size_t)(Np - j0) * NBp))) break;
+            for (size_t i = 0; i < nl; ++i) {
+                gpb200_handle* q = L[i];
+                ++q->launches;
+                cudaError_t e = shard_transpose(q->P[2 * set + 1] + j0, Np, q->P[2 * set] + (size_t)j0 * NBp, NBp, Np - j0, nb, q->st);
+                if (e == cudaSuccess && k > 0 && q->rank == (k - 1) % R) {
+                    // narrow TRTRI update: the accumulator rows of block k-1 (the next panel to be finalised)
+                    if (ev_trtri1[i]) e = cudaStreamWaitEvent(q->st, ev_trtri1[i], 0);           // main(k+1)'s TRTRI part adds into the same rows
+                    GemmDesc g = gemm_desc_default();
+                    g.A = GemmOperand{bufF(q), bufNone(), j0p, j0};
+                    g.B = GemmOperand{bufP(q, 2 * set), bufNone(), j0, 0};
+                    g.C = q->G; g.ldc = q->ld; g.c_row0 = j0p; g.c_col0 = j0;
+                    g.M = NBp; g.N = Np - j0; g.K = nb;
+                    g.alpha = 1.0; g.beta = 1.0;
+                    if (e == cudaSuccess) e = launch_gemm(q, g);
+                }
+                if (e != cudaSuccess) { q->err = cudaGetErrorString(e); rc = GPB200_ECUDA; break; }
+            }
+        } while (false);
+        if (!rc) {
+            for (size_t i = 0; i < nl; ++i) {
+                ev_panel[i] = ring_event(L[i]);
+                if (cudaEventRecord(ev_panel[i], L[i]->st) != cudaSuccess) { L[i]->err = "cudaEventRecord failed"; rc = GPB200_ECUDA; }
+            }
+        }
+        for (auto* q : L) std::swap(q->st, q->st_side);
+        if (rc) { if (L[0]->err.empty()) for (auto* q : L) if (!q->err.empty()) { L[0]->err = q->err; break; } return rc; }
+        // ---------------- main streams: bulk of panel k ----------------
+        for (size_t i = 0; i < nl; ++i) {
+            gpb200_handle* q = L[i];
+            SCK(q, cudaStreamWaitEvent(q->st, ev_panel[i], 0));
+            if (j0p > 0) {   // TRTRI part for the own rows before block k-1
+                GemmDesc g = gemm_desc_default();
+                g.A = GemmOperand{bufF(q), bufNone(), 0, j0};
+                g.B = GemmOperand{bufP(q, 2 * set), bufNone(), j0, 0};
+                g.C = q->G; g.ldc = q->ld; g.c_row0 = 0; g.c_col0 = j0;
+                g.M = j0p; g.N = Np - j0; g.K = nb;
+                g.alpha = 1.0; g.beta = 1.0;
+                own_rows_filter(q, g, 0);
+                SCK(q, launch_gemm(q, g));
+            }
+            cudaEvent_t et = ring_event(q);
+            SCK(q, cudaEventRecord(et, q->st));
+            {   // LAUUM part of panel k for the own rows >= j0
+                GemmDesc g = gemm_desc_default();
+                g.A = GemmOperand{bufG(q), bufDinvT(q), j0, j0};
+                g.B = GemmOperand{bufXR(q, set), bufNone(), 0, j0};
+                g.C = q->G; g.ldc = q->ld; g.c_row0 = j0; g.c_col0 = j0;
+                g.M = Np - j0; g.N = nb; g.K = Np - j0;
+                g.flags = GEMM_LOWER_ONLY | GEMM_KLO_M;
+                own_rows_filter(q, g, j0);
+                SCK(q, launch_gemm(q, g));
+            }
+            cudaEvent_t ef = ring_event(q);
+            SCK(q, cudaEventRecord(ef, q->st));
+            ev_full2[i] = ev_full1[i]; ev_full1[i] = ef; ev_trtri1[i] = et;
         }
     }
     return GPB200_OK;

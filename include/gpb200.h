@@ -157,6 +157,8 @@ int64_t gpb200_launch_count(gpb200_handle* h);
  *                <= 8 dimensions, 0 = always the generic kernel-program kernels (cross-check)
  *   "shard"      multi-GPU storage of the two N x N buffers: 1 = row-sharded (each rank maps only its own block rows),
  *                0 = replicated, -1 (default) = sharded only when the replicated form would not fit the device
+ *   "shard_la"   1 (default) = look-ahead schedules of the row-sharded Cholesky / inverse (panel chain on a side stream),
+ *                0 = the plain one-stream schedules (cross-check)
  *   "shard_rb"   row-sharded ownership block in 128-row tiles (panel width 128*rb): 0 auto, 1, 2, 4, 8
  * Returns GPB200_EINVAL for unknown keys or values.                                           */
 int  gpb200_set_option(gpb200_handle* h, const char* key, int64_t value);

@@ -17,19 +17,21 @@ def _rel(a, b):
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
 
 
-def _group_gp(R, rb, X, y, kern, mean, ln):
+def _group_gp(R, rb, X, y, kern, mean, ln, la=1):
     import gpb200
     eng = gpb200.LocalGroupEngine(R, rb=rb)
+    eng.set_option("shard_la", la)                   # 1: look-ahead schedules (panel chain on a side stream), 0: plain
     return gpb200.GPE(X.T, y, mean, kern, ln, engine=eng), eng
 
 
-@pytest.mark.parametrize("R,rb,N", [(2, 1, 700), (2, 4, 1500), (3, 2, 1500), (4, 1, 1100), (4, 2, 2300), (8, 1, 2100), (2, 8, 2500)])
-def test_sharded_group_matches_oracle(R, rb, N):
+@pytest.mark.parametrize("R,rb,N,la", [(2, 1, 700, 1), (2, 4, 1500, 0), (2, 4, 1500, 1), (3, 2, 1500, 1), (4, 1, 1100, 0), (4, 1, 1100, 1),
+                                       (4, 2, 2300, 1), (8, 1, 2100, 1), (2, 8, 2500, 1), (8, 2, 4200, 1)])
+def test_sharded_group_matches_oracle(R, rb, N, la):
     import gpb200
     d = 3
     X, y, Xs = make_data(N, d, 100 + R + rb, m=130)
     kern = gpb200.SEIso(0.3, 0.1) if (R + rb) % 2 == 0 else gpb200.Mat32Iso(0.2, 0.1) + gpb200.RQIso(0.4, -0.3, 0.2)
-    gp, eng = _group_gp(R, rb, X, y, kern, gpb200.MeanConst(0.2), -0.5)
+    gp, eng = _group_gp(R, rb, X, y, kern, gpb200.MeanConst(0.2), -0.5, la)
     info = [e.storage_info() for e in eng.engines]
     assert all(i["sharded"] and i["nranks"] == R and i["rb"] == rb and i["tma"] for i in info), info
     gp.update_target_and_dtarget()
@@ -55,8 +57,10 @@ def test_sharded_group_matches_oracle(R, rb, N):
     mu2, cov = gp.predict_f(Xs.T[:, :40], full_cov=True)
     _, co = orc.predict_f(kern.spec(), X, o, Xs[:40], ("MeanConst", 0.2), full_cov=True)
     assert np.max(np.abs(cov - co)) <= 1e-9 * np.max(np.abs(co)) + 1e-12
-    # a second evaluation with new hyper-parameters reuses the storage
-    gp.set_params(gp.get_params() + 0.05)
+    # further evaluations with new hyper-parameters reuse the storage (and must not race with the previous schedules)
+    gp.set_params(gp.get_params() + 0.02)
+    gp.update_target_and_dtarget()
+    gp.set_params(gp.get_params() + 0.03)
     gp.update_target_and_dtarget()
     k2 = kern.spec()
     o2 = orc.mll_and_dmll(k2, X, y, gp.logNoise, gp.mean.spec())
