@@ -74,11 +74,16 @@ struct gpb200_handle {
     double *part = nullptr, *trace_out = nullptr;
     double* tblk = nullptr;                    // Npad scratch vector (block right-hand sides of the sharded solves)
     // TMA-staged SEIso kernels (gram_fast.cu): inputs stored [Npad x dxp] with an even, zero-padded dxp <= 8
-    double* xp = nullptr;
+    double *xp = nullptr, *xpt = nullptr;      // [Npad x dxp] and its transpose [dxp x Npad]
     int dxp = 0;
-    CUtensorMap mapX{};
+    CUtensorMap mapX{}, mapXT{};
     bool xmap_ok = false;
     int gram_fast = 1;                         // option "gram_fast": 0 = always the generic kernels of gram.cu
+    // cross-validation (gpb200_cv_*): K_y^-1 mirrored to a full symmetric matrix in G; two N x N temporaries
+    bool g_sym = false;
+    double *cvD = nullptr, *cvY = nullptr;
+    CUtensorMap mapCvD{}, mapCvY{};
+    double* cvblk = nullptr; long long* cvidx = nullptr; int64_t cvblk_cap = 0;
     // posterior sampling (gpb200_rand): M x M sub-engine for chol(Sigma* + nugget I), normal draws / samples staging
     gpb200_handle* sub = nullptr;
     bool cov_keep_device = false;              // predict: leave the full covariance in Kss (no D2H)
@@ -179,6 +184,7 @@ struct gpb200_fitc {
     double *gpart = nullptr, *gacc = nullptr, *gtmp = nullptr;
     CUtensorMap mapAt{}, mapC{}, mapCt{}, mapH{}, mapT{};
     bool grad_ws = false;
+    double* Kss = nullptr; int64_t Kss_rows = 0;      // full predictive covariance (gpb200_fitc_predict_cov)
     int mode = 0;                    // 0 FITC, 1 DTC, 2 SoR (Lambda = sigma^2 I; SoR also drops K_xx - Q_xx from the predictive variance)
     double noise_var = 0.0;
     bool has_data = false, has_kernel = false, factored = false, alpha_ready = false;
@@ -270,8 +276,13 @@ void free_data(gpb200_handle* h) {
     free_FG(h);
     double** ptrs[] = {&h->x, &h->Dinv, &h->DinvT, &h->logd, &h->noise_var, &h->r0, &h->r1,
                        &h->y1, &h->alpha, &h->scal, &h->part, &h->trace_out, &h->xs, &h->Kst, &h->Kss,
-                       &h->pmu, &h->pvar, &h->pkdiag, &h->tblk, &h->xp};
+                       &h->pmu, &h->pvar, &h->pkdiag, &h->tblk, &h->xp, &h->xpt};
     h->xmap_ok = false;
+    if (h->cvD) cudaFree(h->cvD);
+    if (h->cvY) cudaFree(h->cvY);
+    if (h->cvblk) cudaFree(h->cvblk);
+    if (h->cvidx) cudaFree(h->cvidx);
+    h->cvD = h->cvY = h->cvblk = nullptr; h->cvidx = nullptr; h->cvblk_cap = 0; h->g_sym = false;
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
     if (h->flags) { cudaFree(h->flags); h->flags = nullptr; }
@@ -940,7 +951,7 @@ bool use_seiso_fast(gpb200_handle* h, SeIsoFast* sf) {
 cudaError_t launch_gram(gpb200_handle* h, double* G, int64_t ldg, int own_tiles, int nranks, int rank, int own_axis) {
     SeIsoFast sf;
     if (use_seiso_fast(h, &sf))
-        return gram_seiso_tma_launch(&h->mapX, h->dxp, sf, h->N, h->Npad, h->noise_var, h->n_noise, h->nugget, G, ldg, h->st,
+        return gram_seiso_tma_launch(&h->mapX, &h->mapXT, h->dxp, sf, h->N, h->Npad, h->noise_var, h->n_noise, h->nugget, G, ldg, h->st,
                                      own_tiles, nranks, rank, own_axis);
     return gram_lower_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->noise_var, h->n_noise, h->nugget, G, ldg, h->st,
                              own_tiles, nranks, rank, own_axis);
@@ -948,7 +959,7 @@ cudaError_t launch_gram(gpb200_handle* h, double* G, int64_t ldg, int own_tiles,
 cudaError_t launch_trace(gpb200_handle* h, int bm_mod, int bm_rem, int bm_div) {
     SeIsoFast sf;
     if (use_seiso_fast(h, &sf))
-        return trace_seiso_tma_launch(&h->mapX, h->dxp, sf, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
+        return trace_seiso_tma_launch(&h->mapX, &h->mapXT, h->dxp, sf, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
                                       bm_mod, bm_rem, bm_div);
     return trace_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, h->alpha, h->G, h->ld, h->part, h->trace_out, h->st,
                         bm_mod, bm_rem, bm_div);
@@ -1174,7 +1185,11 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
         CK(cudaMemsetAsync(h->xp, 0, sizeof(double) * Npad * h->dxp, h->st));
         CK(cudaMemcpy2DAsync(h->xp, sizeof(double) * h->dxp, x, sizeof(double) * ldx, sizeof(double) * d, N,
                              cudaMemcpyHostToDevice, h->st));
-        h->xmap_ok = gemm_make_tensor_map_plain(&h->mapX, h->xp, N, h->dxp, h->dxp, TILE, h->dxp);
+        if (!h->xpt) CK(cudaMalloc(&h->xpt, sizeof(double) * Npad * h->dxp));
+        ++h->launches;
+        CK(shard_transpose(h->xpt, Npad, h->xp, h->dxp, Npad, h->dxp, h->st));
+        h->xmap_ok = gemm_make_tensor_map_plain(&h->mapX, h->xp, N, h->dxp, h->dxp, TILE, h->dxp) &&
+                     gemm_make_tensor_map_plain(&h->mapXT, h->xpt, h->dxp, N, Npad, h->dxp, TILE);
     }
     CK(cudaStreamSynchronize(h->st));
     h->has_data = true;
@@ -1248,7 +1263,7 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
     for (int i = 0; i < h->prog.n_theta; ++i)
         if (!isfinite(theta[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite hyper-parameter");
     CK(cudaSetDevice(h->device));
-    h->factored = h->inv_ready = h->alpha_ready = false;
+    h->factored = h->inv_ready = h->alpha_ready = false; h->g_sym = false;
     std::vector<double> nv((size_t)n_noise);
     for (int64_t i = 0; i < n_noise; ++i) {
         if (!isfinite(log_noise[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite logNoise");
@@ -1400,6 +1415,7 @@ int gpb200_grad_prepare(gpb200_handle* h) {
     if (!h) return GPB200_EINVAL;
     if (!h->factored) return fail(h, GPB200_ESTATE, "grad_prepare: factorize first");
     if (h->inv_ready) return GPB200_OK;
+    h->g_sym = false;
     CK(cudaSetDevice(h->device));
     CK(cudaEventRecord(h->ev0, h->st));
     if (h->sharded) {
@@ -1626,6 +1642,93 @@ int gpb200_rand(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, con
     ++h->launches;
     CK(add_rowvec_launch(h->rout, ldz, h->pmu, nsamp, M, h->st));                          // + mu (K*' alpha part)
     CK(cudaMemcpy2DAsync(samples, sizeof(double) * M, h->rout, sizeof(double) * ldz, sizeof(double) * M, nsamp, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return GPB200_OK;
+}
+
+// ---- cross-validation on the resident inverse (src/crossvalidation.jl) --------------------------------------------
+// The reference forms inv(Sigma) and, per hyper-parameter j, Z_j = inv(Sigma) dK_j and Z_j inv(Sigma) on the host
+// (crossvalidation.jl:86-108, 270-283).  Here K_y^-1 already sits on the device after gpb200_grad_prepare; per parameter:
+// D = dK_j (recomputed from x), Y' = K^-1 D, M_j = Y' K^-1 -- two NT DMMA GEMMs -- and the two N-vectors every LOO / fold
+// formula needs: Z_j alpha = Y' alpha and diag(M_j).  Fold formulas read principal sub-blocks through gpb200_cv_block.
+static int cv_prepare(gpb200_handle* h) {
+    if (!h->inv_ready) return fail(h, GPB200_ESTATE, "cv: grad_prepare first (K_y^-1 must be resident)");
+    if (h->nranks > 1) return fail(h, GPB200_ESTATE, "cv: K^-1 is distributed over the ranks; single-GPU handles only");
+    const size_t nn = sizeof(double) * (size_t)h->Npad * (size_t)h->Npad;
+    if (!h->cvD) {
+        CK(cudaMalloc(&h->cvD, nn));
+        CK(cudaMalloc(&h->cvY, nn));
+        if (h->tma_ok && !(gemm_make_tensor_map(&h->mapCvD, h->cvD, h->Npad, h->Npad, h->Npad) &&
+                           gemm_make_tensor_map(&h->mapCvY, h->cvY, h->Npad, h->Npad, h->Npad)))
+            return fail(h, GPB200_ECUDA, "cv: cuTensorMapEncodeTiled failed");
+    }
+    if (!h->g_sym) {
+        ++h->launches;
+        CK(symmetrize_launch(h->G, h->ld, h->Npad, h->st));      // lower K^-1 -> full symmetric (the W' scratch above it is dead)
+        h->g_sym = true;
+    }
+    return GPB200_OK;
+}
+
+int gpb200_cv_param(gpb200_handle* h, int32_t param, const double* alpha, double* Zj_alpha, double* diag_ZjSinv) {
+    if (!h || !Zj_alpha || !diag_ZjSinv) return GPB200_EINVAL;
+    if (param < -1 || param >= h->prog.n_theta) return fail(h, GPB200_EINVAL, "cv_param: parameter index out of range");
+    if (!alpha && !h->alpha_ready) return fail(h, GPB200_ESTATE, "cv_param: no alpha (call mll or pass alpha)");
+    CK(cudaSetDevice(h->device));
+    int rc = cv_prepare(h);
+    if (rc) return rc;
+    if (alpha) { rc = upload_padded(h, h->alpha, alpha); if (rc) return rc; h->alpha_ready = true; }
+    const int Np = (int)h->Npad;
+    GemmBuf bD{h->tma_ok ? &h->mapCvD : nullptr, h->cvD, h->Npad}, bY{h->tma_ok ? &h->mapCvY : nullptr, h->cvY, h->Npad};
+    const double* Yt = h->cvY;
+    if (param >= 0) {
+        ++h->launches;
+        CK(gram_grad_full_launch(h->prog, h->x, h->d, h->d, h->N, h->Npad, param, h->cvD, h->Npad, h->st));
+        GemmDesc g = gemm_desc_default();                           // Y' = K^-1 D   (both symmetric: NT form)
+        g.A = GemmOperand{bufG(h), bufNone(), 0, 0};
+        g.B = GemmOperand{bD, bufNone(), 0, 0};
+        g.C = h->cvY; g.ldc = h->Npad; g.M = Np; g.N = Np; g.K = Np;
+        CK(launch_gemm(h, g));
+    } else {
+        Yt = h->G;                                                  // noise: Z = K^-1 (crossvalidation.jl:124-126)
+    }
+    h->launches += 2;
+    CK(rowdot_launch(Yt, h->Npad, h->alpha, h->N, h->Npad, h->r1, h->st));              // Z_j alpha
+    CK(rowdot2_launch(h->G, Yt, h->Npad, h->N, h->Npad, h->y1, h->st));                 // diag(Z_j K^-1) = rowwise <K^-1_i, Y'_i>
+    {   // M_j = Y' K^-1  -> cvD (fold sub-blocks)
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{param >= 0 ? bY : bufG(h), bufNone(), 0, 0};
+        g.B = GemmOperand{bufG(h), bufNone(), 0, 0};
+        g.C = h->cvD; g.ldc = h->Npad; g.M = Np; g.N = Np; g.K = Np;
+        CK(launch_gemm(h, g));
+    }
+    CK(cudaMemcpyAsync(Zj_alpha, h->r1, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(diag_ZjSinv, h->y1, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    profile_collect(h);
+    return GPB200_OK;
+}
+
+int gpb200_cv_block(gpb200_handle* h, int32_t which, int64_t nV, const int64_t* idx, double* out) {
+    if (!h || !idx || !out || nV <= 0 || which < 0 || which > 1) return GPB200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    int rc = cv_prepare(h);
+    if (rc) return rc;
+    for (int64_t a = 0; a < nV; ++a)
+        if (idx[a] < 0 || idx[a] >= h->N) return fail(h, GPB200_EINVAL, "cv_block: index out of range");
+    if (nV > h->cvblk_cap) {
+        if (h->cvblk) cudaFree(h->cvblk);
+        if (h->cvidx) cudaFree(h->cvidx);
+        h->cvblk = nullptr; h->cvidx = nullptr; h->cvblk_cap = 0;
+        CK(cudaMalloc(&h->cvblk, sizeof(double) * nV * nV));
+        CK(cudaMalloc(&h->cvidx, sizeof(long long) * nV));
+        h->cvblk_cap = nV;
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "index width");
+    CK(cudaMemcpyAsync(h->cvidx, idx, sizeof(long long) * nV, cudaMemcpyHostToDevice, h->st));
+    ++h->launches;
+    CK(gather_block_launch(h->cvblk, which == 0 ? h->G : h->cvD, h->Npad, h->cvidx, nV, h->st));
+    CK(cudaMemcpyAsync(out, h->cvblk, sizeof(double) * nV * nV, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return GPB200_OK;
 }
@@ -1876,6 +1979,7 @@ void gpb200_fitc_destroy(gpb200_fitc* f) {
                        &f->bvec, &f->uvec, &f->tmpm, &f->rhsm, &f->scal, &f->bufA, &f->bufB,
                        &f->bufC, &f->Hbuf, &f->Wbuf, &f->Tbuf, &f->gvec, &f->betav, &f->gpart, &f->gacc, &f->gtmp};
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    if (f->Kss) cudaFree(f->Kss);
     if (f->es) { f->es->st = nullptr; f->es->own_stream = false; gpb200_destroy(f->es); }
     if (f->eu) gpb200_destroy(f->eu);
     delete f;
@@ -2127,6 +2231,58 @@ int gpb200_fitc_predict(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ld
     return GPB200_OK;
 }
 
+
+// predictMVN with the FULL predictive covariance (fitc.jl:324-332 -> determ_train_conditional.jl:41-59 ->
+// subsetofregressors.jl:302-321):  Sigma* = K** - K*u K_uu^-1 Ku* + K*u S^-1 Ku*   (FITC, DTC);   K*u S^-1 Ku*   (SoR)
+// = K** - A A' + B B' with A = K*u L_uu^-T, B = K*u L_s^-T: two whitening TRSMs and two NT GEMMs.  Ms <= one staging chunk.
+int gpb200_fitc_predict_cov(gpb200_fitc* f, int64_t Ms, const double* xs, int64_t ldxs, double* mu, double* cov) {
+    if (!f || Ms <= 0 || !xs || ldxs < f->d || !mu || !cov) return GPB200_EINVAL;
+    if (!f->factored || !f->alpha_ready) { f->err = "fitc_predict_cov: factorize and mll first"; return GPB200_ESTATE; }
+    if (Ms > f->Nc) { f->err = "fitc_predict_cov: too many test points for one staging chunk"; return GPB200_EINVAL; }
+    FCK(cudaSetDevice(f->device));
+    gpb200_handle *eu = f->eu, *es = f->es;
+    cudaStream_t st = eu->st;
+    const int64_t Mspad = (Ms + TILE - 1) / TILE * TILE;
+    if (Mspad > f->Kss_rows) {
+        if (f->Kss) cudaFree(f->Kss);
+        f->Kss = nullptr; f->Kss_rows = 0;
+        FCK(cudaMalloc(&f->Kss, sizeof(double) * Mspad * Mspad));
+        f->Kss_rows = Mspad;
+    }
+    GemmBuf bA{eu->tma_ok ? &f->mapA : nullptr, f->bufA, f->Mpad};
+    GemmBuf bB2{eu->tma_ok ? &f->mapB2 : nullptr, f->bufB, f->Mpad};
+    FCK(cudaMemcpy2DAsync(f->xs, sizeof(double) * f->d, xs, sizeof(double) * ldxs, sizeof(double) * f->d, Ms, cudaMemcpyHostToDevice, st));
+    FCK(fitc_kfu(f, f->xs, Ms));                                         // bufA = K*u  (Ms x Mpad, zero padded rows)
+    ++eu->launches;
+    FCK(rowdot_launch(f->bufA, f->Mpad, f->uvec, Ms, f->Mpad, f->tmpc, st));
+    FCK(cudaMemcpyAsync(mu, f->tmpc, sizeof(double) * Ms, cudaMemcpyDeviceToHost, st));
+    FCK(cudaMemcpyAsync(f->bufB, f->bufA, sizeof(double) * f->Nc * f->Mpad, cudaMemcpyDeviceToDevice, st));
+    FCK(trsm_rec_buf(es, bB2, (int)Mspad, 0, (int)f->Mpad));             // B = K*u L_s^-T
+    ++eu->launches;
+    if (f->mode != 2) {
+        FCK(trsm_rec_buf(eu, bA, (int)Mspad, 0, (int)f->Mpad));         // A = K*u L_uu^-T
+        FCK(gram_full_launch(eu->prog, f->xs, f->d, Ms, Mspad, f->d, f->Kss, Mspad, st));
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bA, bufNone(), 0, 0};
+        g.B = GemmOperand{bA, bufNone(), 0, 0};
+        g.C = f->Kss; g.ldc = Mspad; g.M = (int)Mspad; g.N = (int)Mspad; g.K = (int)f->Mpad;
+        g.alpha = -1.0; g.beta = 1.0;
+        FCK(launch_gemm(eu, g));
+    } else {
+        FCK(cudaMemsetAsync(f->Kss, 0, sizeof(double) * Mspad * Mspad, st));
+    }
+    {
+        GemmDesc g = gemm_desc_default();
+        g.A = GemmOperand{bB2, bufNone(), 0, 0};
+        g.B = GemmOperand{bB2, bufNone(), 0, 0};
+        g.C = f->Kss; g.ldc = Mspad; g.M = (int)Mspad; g.N = (int)Mspad; g.K = (int)f->Mpad;
+        g.alpha = 1.0; g.beta = 1.0;
+        FCK(launch_gemm(es, g));
+    }
+    FCK(cudaMemcpy2DAsync(cov, sizeof(double) * Ms, f->Kss, sizeof(double) * Mspad, sizeof(double) * Ms, Ms, cudaMemcpyDeviceToHost, st));
+    FCK(cudaStreamSynchronize(st));
+    return GPB200_OK;
+}
 
 // Kernel-parameter gradient of the FITC mll: dmll_kern!(::FullyIndepStrat) (fitc.jl:200-234) on top of
 // dmll_kern!(::SubsetOfRegsStrategy) (subsetofregressors.jl:219-253), regrouped so that every

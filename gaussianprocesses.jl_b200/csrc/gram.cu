@@ -224,6 +224,36 @@ __global__ void __launch_bounds__(NT) gram_full_kernel(const __grid_constant__ K
     }
 }
 
+// dK/dtheta_j as a full symmetric matrix (N_pad x N_pad, zero padding): grad_slice! of the reference
+// (/root/reference/src/kernels/kernels.jl:96-131), needed by the cross-validation gradients (src/crossvalidation.jl:67-170, 253-341)
+__global__ void __launch_bounds__(NT) gram_grad_full_kernel(const __grid_constant__ KProg P, const double* __restrict__ x, long long ldx,
+                                                            long long N, int d, int j, double* __restrict__ D, long long ldd) {
+    const int bm = blockIdx.y, bn = blockIdx.x;
+    extern __shared__ double sm[];
+    const int ds = d | 1;
+    double* sXi = sm;
+    double* sXj = sm + TB * ds;
+    load_xtile(sXi, x, ldx, d, ds, (long long)bm * TB, N);
+    load_xtile(sXj, x, ldx, d, ds, (long long)bn * TB, N);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double gbuf[GPB200_MAX_THETA];
+#pragma unroll 1
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp * 16 + rr;
+        const long long gi = (long long)bm * TB + r;
+        const double* xi = sXi + r * ds;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+            const int c = (b >> 1) * 64 + lane * 2 + (b & 1);
+            const long long gj = (long long)bn * TB + c;
+            double v = 0.0;
+            if (gi < N && gj < N) { kprog_eval<true>(P, xi, sXj + c * ds, gbuf); v = gbuf[j]; }
+            D[gi * ldd + gj] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // fused gradient trace over the lower triangle of Kinv (tile-per-CTA):
 //   part[tile][p]        = sum_{i>j in tile} A_ij dK_ij/dθ_p + 1/2 sum_{i==j} A_ii dK_ii/dθ_p
@@ -532,5 +562,16 @@ cudaError_t trace_rect_launch(const KProg& P, const double* x1, int64_t ldx1, in
 cudaError_t kdiag_grad_launch(const KProg& P, const double* x, int64_t ldx, int64_t N, const double* gvec, double* out,
                               cudaStream_t st) {
     kdiag_grad_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(P, x, ldx, N, gvec, out);
+    return cudaGetLastError();
+}
+
+cudaError_t gram_grad_full_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad, int j,
+                                  double* D, int64_t ldd, cudaStream_t st) {
+    if (j < 0 || j >= P.n_theta) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)(Npad / TB), (unsigned)(Npad / TB));
+    const size_t sm = xtile_smem(d);
+    cudaError_t e;
+    if ((e = ensure_smem(gram_grad_full_kernel, sm)) != cudaSuccess) return e;
+    gram_grad_full_kernel<<<grid, NT, sm, st>>>(P, x, ldx, N, d, j, D, ldd);
     return cudaGetLastError();
 }

@@ -44,7 +44,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                  : "memory");
 }
 
-// sigma^2 * 2^z for z <= 0 (clamped at -960: values below 1e-289 sigma^2 are returned as ~1e-289 sigma^2)
+// sigma^2 * 2^z for z <= 0 (clamped at -960: values below 1e-289 sigma^2 are returned as ~1e-289 sigma^2).
+// The 32-entry table is replicated 16 times in shared memory, entry j of copy c at word j*16 + c, and lane l reads copy
+// l % 16: the 16 lanes of a half-warp always hit 16 different bank pairs, whatever their indices (the plain 32-entry table
+// cost ~9 extra LSU cycles per lookup in bank conflicts: ncu l1tex__data_bank_conflicts 154 M per launch at C2).
 __device__ __forceinline__ double exp2_tab(double z, const double* __restrict__ tab) {
     z = fmax(z, -960.0);
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: the low mantissa bits hold round(32 z)
@@ -59,7 +62,7 @@ __device__ __forceinline__ double exp2_tab(double z, const double* __restrict__ 
     p = fma(p, f, 2.4022650695910071233e-1);                  // ln2^2 / 2
     p = fma(p, f, 6.9314718055994530942e-1);                  // ln2
     p = fma(p, f, 1.0);
-    const double r = tab[ki & 31] * p;
+    const double r = tab[(ki & 31) << 4] * p;                 // tab already points at this lane's copy (bank pair lane % 16)
     return __hiloint2double(__double2hiint(r) + ((ki >> 5) << 20), __double2loint(r));
 }
 
@@ -71,8 +74,10 @@ __device__ __forceinline__ void tri_decode(int lin, int& bm, int& bn) {
 }
 
 // stage the two 128 x DX input tiles by TMA; returns true if every staged value is finite
+// row tile sXi[r][k] from x (N x DX), column tile sXjT[k][c] from the transposed copy x' (DX x N): the per-lane register
+// preload of column points then reads 16 consecutive bytes per lane (conflict-free), the row points are broadcast reads.
 template <int DX>
-__device__ __forceinline__ bool stage_tiles(const CUtensorMap* mapX, double* sXi, double* sXj, uint64_t* bar, int bm, int bn) {
+__device__ __forceinline__ bool stage_tiles(const CUtensorMap* mapX, const CUtensorMap* mapXT, double* sXi, double* sXj, uint64_t* bar, int bm, int bn) {
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -82,7 +87,7 @@ __device__ __forceinline__ bool stage_tiles(const CUtensorMap* mapX, double* sXi
     if (threadIdx.x == 0) {
         mbar_expect_tx(bar, 2u * TB * DX * 8u);
         tma_load_2d(sXi, mapX, bar, 0, bm * TB);
-        tma_load_2d(sXj, mapX, bar, 0, bn * TB);
+        tma_load_2d(sXj, mapXT, bar, bn * TB, 0);
     }
     mbar_wait(bar, 0);
     int bad = 0;
@@ -92,26 +97,28 @@ __device__ __forceinline__ bool stage_tiles(const CUtensorMap* mapX, double* sXi
 
 template <int DX>
 __global__ void __launch_bounds__(NT, 2)
-gram_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ SeIsoFast sf, long long N,
+gram_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXT,
+                      const __grid_constant__ SeIsoFast sf, long long N,
                       const double* __restrict__ noise_var, long long n_noise, double nugget, double* __restrict__ G,
                       long long ldg, int own_tiles, int nranks, int rank, int own_axis) {
     __shared__ __align__(128) double sXi[TB * DX];
     __shared__ __align__(128) double sXj[TB * DX];
-    __shared__ double sTab[32];
+    __shared__ double sTabR[32 * 16];
     __shared__ __align__(8) uint64_t bar;
     int bm, bn;
     tri_decode(blockIdx.x, bm, bn);
     if (own_tiles > 0 && (((own_axis ? bm : bn) / own_tiles) % nranks) != rank) return;
-    if (threadIdx.x < 32) sTab[threadIdx.x] = sf.tab[threadIdx.x];
-    const bool finite = stage_tiles<DX>(&mapX, sXi, sXj, &bar, bm, bn);
+    for (int i = threadIdx.x; i < 32 * 16; i += NT) sTabR[i] = sf.tab[i >> 4];
+    const double* sTab = sTabR + (threadIdx.x & 15);
+    const bool finite = stage_tiles<DX>(&mapX, &mapXT, sXi, sXj, &bar, bm, bn);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double xj[4][DX];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int c = (q >> 1) * 64 + lane * 2 + (q & 1);
-#pragma unroll
-        for (int k = 0; k < DX; ++k) xj[q][k] = sXj[c * DX + k];
+    for (int k = 0; k < DX; ++k) {
+        const double2 lo = *reinterpret_cast<const double2*>(sXj + k * TB + lane * 2);
+        const double2 hi = *reinterpret_cast<const double2*>(sXj + k * TB + 64 + lane * 2);
+        xj[0][k] = lo.x; xj[1][k] = lo.y; xj[2][k] = hi.x; xj[3][k] = hi.y;
     }
     const bool plain = finite && (bm != bn) && ((long long)(bm + 1) * TB <= N);
     const double c_hi = sf.c_hi, c_lo = sf.c_lo;
@@ -165,12 +172,13 @@ gram_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
 // w = A below the diagonal, A/2 on it  (GPE.jl:219-241, 273-275)
 template <int DX>
 __global__ void __launch_bounds__(NT, 2)
-trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ SeIsoFast sf, long long N,
+trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXT,
+                       const __grid_constant__ SeIsoFast sf, long long N,
                        const double* __restrict__ alpha, const double* __restrict__ Kinv, long long ldg,
                        double* __restrict__ part, int bm_mod, int bm_rem, int bm_div) {
     __shared__ __align__(128) double sXi[TB * DX];
     __shared__ __align__(128) double sXj[TB * DX];
-    __shared__ double sTab[32];
+    __shared__ double sTabR[32 * 16];
     __shared__ double sAi[TB], sAj[TB];
     __shared__ double sRed[8 * 3];
     __shared__ __align__(8) uint64_t bar;
@@ -181,22 +189,24 @@ trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
         if (threadIdx.x < 3) part[lin * 3 + threadIdx.x] = 0.0;
         return;
     }
-    if (threadIdx.x < 32) sTab[threadIdx.x] = sf.tab[threadIdx.x];
+    for (int i = threadIdx.x; i < 32 * 16; i += NT) sTabR[i] = sf.tab[i >> 4];
+    const double* sTab = sTabR + (threadIdx.x & 15);
     if (threadIdx.x < TB) {
         const long long gi = (long long)bm * TB + threadIdx.x, gj = (long long)bn * TB + threadIdx.x;
         sAi[threadIdx.x] = gi < N ? alpha[gi] : 0.0;
         sAj[threadIdx.x] = gj < N ? alpha[gj] : 0.0;
     }
-    const bool finite = stage_tiles<DX>(&mapX, sXi, sXj, &bar, bm, bn);
+    const bool finite = stage_tiles<DX>(&mapX, &mapXT, sXi, sXj, &bar, bm, bn);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double xj[4][DX], aj[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int c = (q >> 1) * 64 + lane * 2 + (q & 1);
-        aj[q] = sAj[c];
+    for (int q = 0; q < 4; ++q) aj[q] = sAj[(q >> 1) * 64 + lane * 2 + (q & 1)];
 #pragma unroll
-        for (int k = 0; k < DX; ++k) xj[q][k] = sXj[c * DX + k];
+    for (int k = 0; k < DX; ++k) {
+        const double2 lo = *reinterpret_cast<const double2*>(sXj + k * TB + lane * 2);
+        const double2 hi = *reinterpret_cast<const double2*>(sXj + k * TB + 64 + lane * 2);
+        xj[0][k] = lo.x; xj[1][k] = lo.y; xj[2][k] = hi.x; xj[3][k] = hi.y;
     }
     const bool plain = finite && (bm != bn) && ((long long)(bm + 1) * TB <= N);
     const double c_hi = sf.c_hi, c_lo = sf.c_lo;
@@ -296,32 +306,32 @@ bool seiso_fast_prepare(double l2, double s2, SeIsoFast* out) {
     return true;
 }
 
-cudaError_t gram_seiso_tma_launch(const CUtensorMap* mapX, int dx, const SeIsoFast& sf, int64_t N, int64_t Npad,
+cudaError_t gram_seiso_tma_launch(const CUtensorMap* mapX, const CUtensorMap* mapXT, int dx, const SeIsoFast& sf, int64_t N, int64_t Npad,
                                   const double* noise_var, int64_t n_noise, double nugget, double* G, int64_t ldg,
                                   cudaStream_t st, int own_tiles, int nranks, int rank, int own_axis) {
     const int T = (int)(Npad / TB);
     const int tiles = T * (T + 1) / 2;
     switch (dx) {
-    case 2: gram_seiso_tma_kernel<2><<<tiles, NT, 0, st>>>(*mapX, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
-    case 4: gram_seiso_tma_kernel<4><<<tiles, NT, 0, st>>>(*mapX, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
-    case 6: gram_seiso_tma_kernel<6><<<tiles, NT, 0, st>>>(*mapX, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
-    case 8: gram_seiso_tma_kernel<8><<<tiles, NT, 0, st>>>(*mapX, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
+    case 2: gram_seiso_tma_kernel<2><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
+    case 4: gram_seiso_tma_kernel<4><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
+    case 6: gram_seiso_tma_kernel<6><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
+    case 8: gram_seiso_tma_kernel<8><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
-cudaError_t trace_seiso_tma_launch(const CUtensorMap* mapX, int dx, const SeIsoFast& sf, int64_t N, int64_t Npad,
+cudaError_t trace_seiso_tma_launch(const CUtensorMap* mapX, const CUtensorMap* mapXT, int dx, const SeIsoFast& sf, int64_t N, int64_t Npad,
                                    const double* alpha, const double* Kinv, int64_t ldg, double* part, double* out,
                                    cudaStream_t st, int bm_mod, int bm_rem, int bm_div) {
     const int T = (int)(Npad / TB);
     const int tiles = T * (T + 1) / 2;
     if (bm_div < 1) bm_div = 1;
     switch (dx) {
-    case 2: trace_seiso_tma_kernel<2><<<tiles, NT, 0, st>>>(*mapX, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
-    case 4: trace_seiso_tma_kernel<4><<<tiles, NT, 0, st>>>(*mapX, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
-    case 6: trace_seiso_tma_kernel<6><<<tiles, NT, 0, st>>>(*mapX, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
-    case 8: trace_seiso_tma_kernel<8><<<tiles, NT, 0, st>>>(*mapX, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
+    case 2: trace_seiso_tma_kernel<2><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
+    case 4: trace_seiso_tma_kernel<4><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
+    case 6: trace_seiso_tma_kernel<6><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
+    case 8: trace_seiso_tma_kernel<8><<<tiles, NT, 0, st>>>(*mapX, *mapXT, sf, N, alpha, Kinv, ldg, part, bm_mod, bm_rem, bm_div); break;
     default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();

@@ -484,3 +484,16 @@ cudaError_t add_rowvec_launch(double* A, int64_t ld, const double* v, int64_t nr
     add_rowvec_kernel<<<grid, 256, 0, st>>>(A, ld, v, nrows, ncols);
     return cudaGetLastError();
 }
+
+namespace {
+__global__ void gather_block_kernel(double* __restrict__ out, const double* __restrict__ src, long long ld, const long long* __restrict__ idx, long long nv) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b < nv) out[a * nv + b] = src[idx[a] * ld + idx[b]];
+}
+}  // namespace
+cudaError_t gather_block_launch(double* out, const double* src, int64_t ld, const long long* idx, int64_t nv, cudaStream_t st) {
+    if (nv <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((nv + 255) / 256), (unsigned)nv);
+    gather_block_kernel<<<grid, 256, 0, st>>>(out, src, ld, idx, nv);
+    return cudaGetLastError();
+}

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "gpb200_grad_kernel": (C.c_int, [_H, _dp, _dp, _dp]),
     "gpb200_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp]),
     "gpb200_rand": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp, C.c_double, _dp, _dp]),
+    "gpb200_cv_param": (C.c_int, [_H, C.c_int32, _dp, _dp, _dp]),
+    "gpb200_cv_block": (C.c_int, [_H, C.c_int32, C.c_int64, C.POINTER(C.c_int64), _dp]),
     "gpb200_get_gram": (C.c_int, [_H, _dp]),
     "gpb200_get_factor": (C.c_int, [_H, _dp]),
     "gpb200_get_inverse": (C.c_int, [_H, _dp]),
@@ -63,6 +65,7 @@ _SIGNATURES = {
     "gpb200_fitc_grad_noise": (C.c_int, [_H, _dp]),
     "gpb200_fitc_grad_kernel": (C.c_int, [_H, _dp]),
     "gpb200_fitc_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp]),
+    "gpb200_fitc_predict_cov": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp]),
     "gpb200_fitc_set_mode": (C.c_int, [_H, C.c_int]),
     "gpb200_fitc_launch_count": (C.c_int64, [_H]),
     "gpb200_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
@@ -228,6 +231,19 @@ class Engine:
         self._check(self._lib.gpb200_rand(self._h, M, _as_dp(xs_pm), d, ap, z.shape[0], _as_dp(z), float(nugget), _as_dp(mu),
                                           _as_dp(out)), "rand")
         return mu, out
+
+    def cv_param(self, param, alpha=None):
+        """(Z_j alpha, diag(Z_j K^-1)) for kernel parameter `param` (index into the full parameter vector) or -1 = noise."""
+        za, dg = np.empty(self.N), np.empty(self.N)
+        ap = _as_dp(np.ascontiguousarray(alpha, dtype=np.float64)) if alpha is not None else None
+        self._check(self._lib.gpb200_cv_param(self._h, int(param), ap, _as_dp(za), _as_dp(dg)), "cv_param")
+        return za, dg
+
+    def cv_block(self, which, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        out = np.empty((idx.size, idx.size))
+        self._check(self._lib.gpb200_cv_block(self._h, int(which), idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), _as_dp(out)), "cv_block")
+        return out
 
     # -- debug ----------------------------------------------------------------------------
     def gram(self):
@@ -402,6 +418,16 @@ class FitcEngine:
         self._check(self._lib.gpb200_fitc_predict(self._h, Ms, _as_dp(xs_pm), d, _as_dp(mu),
                                                   _as_dp(var) if want_var else None), "fitc_predict")
         return mu, var
+
+    def predict_cov(self, xs_pm):
+        xs_pm = np.ascontiguousarray(xs_pm, dtype=np.float64)
+        Ms, d = xs_pm.shape
+        if d != self.d:
+            raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
+        mu = np.empty(Ms)
+        cov = np.empty((Ms, Ms))
+        self._check(self._lib.gpb200_fitc_predict_cov(self._h, Ms, _as_dp(xs_pm), d, _as_dp(mu), _as_dp(cov)), "fitc_predict_cov")
+        return mu, cov
 
     def set_mode(self, mode):
         """0 FITC, 1 DTC, 2 SoR."""

@@ -199,6 +199,79 @@ class GPE:
         mu, s2 = self.predict_LOO()
         return float(np.sum(-0.5 * np.log(2.0 * np.pi * s2) - 0.5 * (self.y - mu) ** 2 / s2))
 
+    # ---- cross-validation on the device's resident K_y^-1 (src/crossvalidation.jl) ------------------------------------
+    def _loo_component(self, Zja, ZjSinv, s2, mu):
+        """body of dlogpdθ_LOO_kern! / dlogpdσ2_LOO for one parameter (crossvalidation.jl:94-107, 130-140), before the -1/2"""
+        ds2 = ZjSinv * s2 ** 2
+        dmu = Zja * s2 - self.alpha * ds2
+        y = self.y
+        return float(-np.sum(2.0 * (y - mu) / s2 * dmu) - np.sum((y - mu) ** 2 * ZjSinv) + np.sum(ZjSinv * s2))
+
+    def dlogp_LOO(self, noise=True, domean=False, kern=True):
+        """dlogpdθ_LOO(gp; noise, domean, kern) (src/crossvalidation.jl:150-178): gradient of the leave-one-out criterion.
+        Per parameter the device forms inv(Σ) dK_j and its product with inv(Σ) (two N^3 GEMMs on the resident inverse) and
+        returns Z_j α and diag(Z_j inv(Σ)); the O(N) assembly below follows the reference line by line."""
+        if domean and self.mean.num_params() > 0:
+            raise NotImplementedError("I don't know how to do means yet")          # crossvalidation.jl:168
+        mu, s2 = self.predict_LOO()
+        out = []
+        if noise:
+            Zja, ZjS = self._eng.cv_param(-1)
+            out.append(-self._loo_component(Zja, ZjS, s2, mu) / 2.0 * 2.0 * math.exp(2.0 * self.logNoise))
+        if kern:
+            for j in self._exposed:
+                Zja, ZjS = self._eng.cv_param(int(j))
+                out.append(-0.5 * self._loo_component(Zja, ZjS, s2, mu))
+        return np.array(out)
+
+    def predict_CVfold(self, folds):
+        """predict_CVfold(gp, folds) (src/crossvalidation.jl:180-218): per fold V the predictive mean / covariance of y_V given
+        the other observations, from the principal sub-block inv(Σ)[V,V] read off the device."""
+        self._eng.grad_prepare()
+        mus, Sigs = [], []
+        for V in folds:
+            V = np.asarray(V, dtype=np.int64)
+            SVT = np.linalg.inv(self._eng.cv_block(0, V))
+            mus.append(self.y[V] - SVT @ self.alpha[V])
+            Sigs.append(SVT)
+        return mus, Sigs
+
+    def logp_CVfold(self, folds):
+        """logp_CVfold(gp, folds) (src/crossvalidation.jl:225-237)."""
+        mus, Sigs = self.predict_CVfold(folds)
+        cv = 0.0
+        for mu, S, V in zip(mus, Sigs, folds):
+            V = np.asarray(V, dtype=np.int64)
+            L = np.linalg.cholesky(S + 1e-10 * np.eye(V.size))                    # make_posdef!(ΣVT; nugget=1e-10)
+            z = np.linalg.solve(L, self.y[V] - mu)
+            cv += -0.5 * (z @ z) - np.sum(np.log(np.diag(L))) - 0.5 * V.size * math.log(2.0 * math.pi)
+        return float(cv)
+
+    def _fold_component(self, Zja, folds, inv_blocks):
+        comp = 0.0
+        for V, SVTinv in zip(folds, inv_blocks):                                   # gradient_fold, crossvalidation.jl:248-262
+            V = np.asarray(V, dtype=np.int64)
+            ZVV = self._eng.cv_block(1, V)
+            SVTa = np.linalg.solve(SVTinv, self.alpha[V])
+            comp += -2.0 * (SVTa @ Zja[V]) + SVTa @ (ZVV @ SVTa) + np.trace(np.linalg.solve(SVTinv, ZVV))
+        return comp
+
+    def dlogp_CVfold(self, folds, noise=True, domean=False, kern=True):
+        """dlogpdθ_CVfold(gp, folds; noise, domean, kern) (src/crossvalidation.jl:264-341)."""
+        if domean and self.mean.num_params() > 0:
+            raise NotImplementedError("I don't know how to do means yet")          # crossvalidation.jl:330
+        self._eng.grad_prepare()
+        inv_blocks = [self._eng.cv_block(0, np.asarray(V, dtype=np.int64)) for V in folds]
+        out = []
+        if noise:
+            Zja, _ = self._eng.cv_param(-1)
+            out.append(-self._fold_component(Zja, folds, inv_blocks) / 2.0 * 2.0 * math.exp(2.0 * self.logNoise))
+        if kern:
+            for j in self._exposed:
+                Zja, _ = self._eng.cv_param(int(j))
+                out.append(-0.5 * self._fold_component(Zja, folds, inv_blocks))
+        return np.array(out)
+
     def rand(self, x, n=1, nugget=1e-10, rng=None):
         """rand(gp, X, n) (src/GP.jl:120-146): n posterior draws at the columns of x, computed on the device (predictive
         covariance, make_posdef!(Σ; nugget) Cholesky, unwhiten!); only the standard-normal draws come from the host RNG,

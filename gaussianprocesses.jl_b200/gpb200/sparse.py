@@ -72,16 +72,21 @@ class FITC:
     def noise_variance(self):
         return math.exp(2.0 * self.logNoise)
 
-    def predict_f(self, x):
+    def predict_f(self, x, full_cov=False):
         x = _as_dxn(x)
         if x.shape[0] != self.dim:
             raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
         xs = np.ascontiguousarray(x.T)
+        if full_cov:                                                   # predict_full -> predictMVN (fitc.jl:324-332)
+            mu, cov = self._eng.predict_cov(xs)
+            return mu + self.mean.mean(xs), cov
         mu, var = self._eng.predict(xs)
         return mu + self.mean.mean(xs), np.maximum(var, 0.0)          # GP.jl:75
 
-    def predict_y(self, x):
-        mu, s2 = self.predict_f(x)
+    def predict_y(self, x, full_cov=False):
+        mu, s2 = self.predict_f(x, full_cov=full_cov)
+        if full_cov:
+            return mu, s2 + self.noise_variance() * np.eye(s2.shape[0])       # GPE.jl:412 (ScalMat)
         return mu, s2 + self.noise_variance()
 
 

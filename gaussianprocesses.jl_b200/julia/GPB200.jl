@@ -15,6 +15,7 @@ module GPB200
 using GaussianProcesses
 using LinearAlgebra
 using PDMats
+import Random
 import GaussianProcesses: CovarianceStrategy, KernelData, EmptyData, alloc_cK, update_cK!, init_precompute,
                           precompute!, dmll_kern!, dmll_noise, predictMVN, predict_f, predict_full,
                           AbstractGradientPrecompute, Kernel, Mean, GPE, get_params, num_params, mean,
@@ -211,6 +212,17 @@ function predictMVN(xpred::AbstractMatrix, xtrain::AbstractMatrix, ytrain::Abstr
     return mu .+ mean(meanf, Matrix{Float64}(xpred)), Sigma_raw
 end
 
+# rand(gp, X, n) (src/GP.jl:120-146) on the device: predictive covariance, make_posdef!(Σ; nugget), unwhiten!
+function Random.rand!(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractMatrix, A::DenseMatrix; nugget=1e-10) where {X,Y,M,K,CS<:B200Covariance,D,P}
+    Xs = Matrix{Float64}(x); Ms = size(Xs, 2); n = size(A, 2)
+    Z = randn(Ms, n); mu = Vector{Float64}(undef, Ms); S = Matrix{Float64}(undef, Ms, n)
+    check(gp.cK, ccall((:gpb200_rand, LIB), Cint,
+                       (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}),
+                       gp.cK.handle, Ms, Xs, size(Xs, 1), Vector{Float64}(gp.alpha), n, Z, Float64(nugget), mu, S), "rand")
+    A .= S .+ mean(gp.mean, Xs)
+    return A
+end
+
 # =====================================================================================================
 # Sparse strategies on the device: FITC / DTC / SoR (src/sparse/*.jl) -> gpb200_fitc_* (one streaming engine)
 #     gp = GPE(x, y, mean, kernel, logNoise, B200Sparse(Xu, :FITC))
@@ -298,9 +310,14 @@ function dmll_kern!(dmll::AbstractVector, gp, ::B200SparsePrecompute, ::B200Spar
     return dmll
 end
 function predict_f(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractMatrix; full_cov::Bool=false) where {X,Y,M,K,CS<:B200Sparse,D,P}
-    full_cov && throw(ArgumentError("B200Sparse: full predictive covariance is not built; use full_cov=false"))
     size(x, 1) == gp.dim || throw(ArgumentError("Gaussian Process object and input observations do not have consistent dimensions"))
     Xs = Matrix{Float64}(x); Ms = size(Xs, 2)
+    if full_cov                                                                    # predictMVN: fitc.jl:324-332, dtc.jl:41-59, sor.jl:302-321
+        mu = Vector{Float64}(undef, Ms); Σ = Matrix{Float64}(undef, Ms, Ms)
+        checks(gp.cK, ccall((:gpb200_fitc_predict_cov, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                            gp.cK.handle, Ms, Xs, size(Xs, 1), mu, Σ), "fitc_predict_cov")
+        return mu .+ mean(gp.mean, Xs), Σ
+    end
     mu = Vector{Float64}(undef, Ms); var = Vector{Float64}(undef, Ms)
     checks(gp.cK, ccall((:gpb200_fitc_predict, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
                         gp.cK.handle, Ms, Xs, size(Xs, 1), mu, var), "fitc_predict")

@@ -385,6 +385,21 @@ def _kdiag(spec, X):
     return out
 
 
+def fitc_predict_full(spec, X, Xu, f, Xs, mspec=("MeanZero",)):
+    """predictMVN with the full covariance: SoR  Σ = Lck'Lck, Lck = whiten(ΣQR, Kux)  (sor.jl:302-321);
+    DTC / FITC  Σ = Σxx - Qxx + Σ_SoR  (dtc.jl:41-59, fitc.jl:324-332)."""
+    import scipy.linalg as sl
+    Kux = cov(spec, Xu, Xs)
+    mx, _ = mean_and_grads(mspec, Xs)
+    mu = mx + Kux.T @ f["alpha_u"]
+    Lck = sl.solve_triangular(f["Us"], Kux, trans="T", lower=False)
+    S_sor = Lck.T @ Lck
+    if f.get("mode", "FITC") == "SoR":
+        return mu, S_sor
+    Lq = sl.solve_triangular(f["Uuu"], Kux, trans="T", lower=False)
+    return mu, cov(spec, Xs, Xs) - Lq.T @ Lq + S_sor
+
+
 def fitc_predict(spec, X, Xu, f, Xs, mspec=("MeanZero",)):
     """predictMVN (fitc.jl:324-332 -> dtc.jl:41-59 -> sor.jl:302-321): mu = mx + Kxu alpha_u;
     Sigma = Kxx - Qxx + Kxu ΣQR^-1 Kux (diagonal returned, clamped at 0 like GP.jl:75)."""
@@ -436,4 +451,108 @@ def fitc_dmll_kern(spec, X, Xu, f):
         Lsl = sl.solve_triangular(Us, Kuf / Lam, trans="T", lower=False)
         T2 = np.sum(dLam / Lam) - np.sum(Lsl * (Lsl * dLam))             # trinvAB  fitc.jl:63-67
         out.append(g + (V2 - T2) / 2.0)
+    return np.array(out)
+
+
+# ----------------------------------------------------------------------------------------------
+# cross-validation (src/crossvalidation.jl) -- literal restatement with host matrices
+# ----------------------------------------------------------------------------------------------
+def _inv_sigma(f):
+    n = f["U"].shape[0]
+    return _potrs_upper(f["U"], np.eye(n))                       # inv(Σ), crossvalidation.jl:9
+
+
+def predict_loo(f, y):
+    """predict_LOO (crossvalidation.jl:8-13): sigma_i^2 = 1 / inv(Σ)_ii ; mu_i = y_i - alpha_i sigma_i^2"""
+    invS = _inv_sigma(f)
+    s2 = 1.0 / np.diag(invS)
+    return -f["alpha"] * s2 + y, s2
+
+
+def logp_loo(f, y):
+    """logp_LOO (crossvalidation.jl:48-55): sum of Normal log-pdfs"""
+    mu, s2 = predict_loo(f, y)
+    return float(np.sum(-0.5 * np.log(2.0 * np.pi * s2) - 0.5 * (y - mu) ** 2 / s2))
+
+
+def _loo_component(invS, alpha, y, Zj):
+    """the per-parameter body of dlogpdθ_LOO_kern! / dlogpdσ2_LOO (crossvalidation.jl:86-108, 124-141), before the -1/2"""
+    s2 = 1.0 / np.diag(invS)
+    mu = -alpha * s2 + y
+    ZjSinv = np.diag(Zj @ invS)
+    ds2 = ZjSinv * s2 ** 2
+    dmu = (Zj @ alpha) * s2 - alpha * ds2
+    out = 0.0
+    out -= np.sum(2.0 * (y - mu) / s2 * dmu)
+    out -= np.sum((y - mu) ** 2 * ZjSinv)
+    out += np.sum(ZjSinv * s2)
+    return out
+
+
+def dlogp_loo(spec, X, y, f, log_noise, noise=True, kern=True):
+    """dlogpdθ_LOO (crossvalidation.jl:150-178): [noise; kernel] (mean parameters are not supported by the reference)"""
+    invS = _inv_sigma(f)
+    alpha = f["alpha"]
+    out = []
+    if noise:
+        out.append(-_loo_component(invS, alpha, y, invS) / 2.0 * 2.0 * math.exp(2.0 * log_noise))
+    if kern:
+        _, grads = cov_and_grads(spec, X, None, want_grad=True)
+        for dK in grads:
+            out.append(-0.5 * _loo_component(invS, alpha, y, invS @ dK))
+    return np.array(out)
+
+
+def predict_cvfold(f, y, folds):
+    """predict_CVfold (crossvalidation.jl:180-191)"""
+    invS = _inv_sigma(f)
+    mus, Sigs = [], []
+    for V in folds:
+        V = np.asarray(V)
+        SVT = np.linalg.inv(invS[np.ix_(V, V)])
+        mus.append(y[V] - SVT @ f["alpha"][V])
+        Sigs.append(SVT)
+    return mus, Sigs
+
+
+def logp_cvfold(f, y, folds):
+    """logp_CVfold (crossvalidation.jl:225-237): multivariate normal log-pdf per fold, nugget 1e-10"""
+    mus, Sigs = predict_cvfold(f, y, folds)
+    cv = 0.0
+    for mu, S, V in zip(mus, Sigs, folds):
+        V = np.asarray(V)
+        S = S + 1e-10 * np.eye(len(V))
+        L = np.linalg.cholesky(S)
+        z = np.linalg.solve(L, y[V] - mu)
+        cv += -0.5 * (z @ z) - np.sum(np.log(np.diag(L))) - 0.5 * len(V) * LOG2PI
+    return float(cv)
+
+
+def _fold_component(invS, alpha, ZjSinv, Zja, V):
+    """gradient_fold (crossvalidation.jl:248-262)"""
+    V = np.asarray(V)
+    SVTinv = invS[np.ix_(V, V)]
+    SVTa = np.linalg.solve(SVTinv, alpha[V])
+    ZVV = ZjSinv[np.ix_(V, V)]
+    out = -2.0 * (SVTa @ Zja[V])
+    out += SVTa @ (ZVV @ SVTa)
+    out += np.trace(np.linalg.solve(SVTinv, ZVV))
+    return out
+
+
+def dlogp_cvfold(spec, X, y, f, log_noise, folds, noise=True, kern=True):
+    """dlogpdθ_CVfold (crossvalidation.jl:264-341): [noise; kernel]"""
+    invS = _inv_sigma(f)
+    alpha = f["alpha"]
+    out = []
+    if noise:
+        Zj = invS
+        comp = sum(_fold_component(invS, alpha, Zj @ invS, Zj @ alpha, V) for V in folds)
+        out.append(-comp / 2.0 * 2.0 * math.exp(2.0 * log_noise))
+    if kern:
+        _, grads = cov_and_grads(spec, X, None, want_grad=True)
+        for dK in grads:
+            Zj = invS @ dK
+            comp = sum(_fold_component(invS, alpha, Zj @ invS, Zj @ alpha, V) for V in folds)
+            out.append(-0.5 * comp)
     return np.array(out)

@@ -143,3 +143,29 @@ def test_fitc_well_conditioned_inducing_set_meets_1e10():
     assert _rel(mu, mo) <= 1e-10 and np.max(np.abs(s2 - vo)) <= 1e-10 * np.max(np.abs(vo)) + 1e-13
     gk = orc.fitc_dmll_kern(k.spec(), X, Xu, o)
     assert np.allclose(gp.dmll[2:], gk, rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["FITC", "DTC", "SoR"])
+def test_sparse_full_predictive_covariance(mode):
+    """predict_f(gp, x; full_cov=true) for the sparse strategies (fitc.jl:324-332, dtc.jl:41-59, sor.jl:302-321)."""
+    import gpb200 as g
+    rng = np.random.default_rng(12)
+    N, M, d = 2000, 90, 2
+    X = rng.uniform(-3, 3, (N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    Xs = rng.uniform(-3, 3, (150, d))
+    k = g.SEIso(-0.3, 0.1) + g.Mat32Iso(0.2, -0.5)
+    cls = {"FITC": g.FITC, "DTC": g.DTC, "SoR": g.SoR}[mode]
+    gp = cls(X.T, Xu.T, y, g.MeanConst(0.1), k, -1.0)
+    o = orc.fitc_fit(k.spec(), X, Xu, y, -1.0, ("MeanConst", 0.1), mode=mode)
+    mu, cov = gp.predict_f(Xs.T, full_cov=True)
+    mo, co = orc.fitc_predict_full(k.spec(), X, Xu, o, Xs, ("MeanConst", 0.1))
+    cond = _cond_kuu(k.spec(), Xu)
+    tol = max(1e-10, 64.0 * cond * EPS)
+    assert _rel(mu, mo) < tol
+    assert np.max(np.abs(cov - co)) <= tol * np.max(np.abs(co)), (np.max(np.abs(cov - co)), tol)
+    assert np.allclose(cov, cov.T, atol=1e-12)
+    _, var = gp.predict_f(Xs.T)
+    assert np.allclose(np.maximum(np.diag(cov), 0.0), var, atol=1e-9)
+    my, cy = gp.predict_y(Xs.T[:, :10], full_cov=True)
+    assert np.allclose(np.diag(cy), np.diag(cov)[:10] + np.exp(-2.0), atol=1e-12)

@@ -1,6 +1,7 @@
 """CPU: pin the oracle against the only known-answer vector the reference tree holds for this path
 (perf/benchmarks/simdata.csv + benchmark_julia.ipynb cell 6), and check its
 analytic gradients against finite differences the way test/kernels.jl:148-164 does."""
+import math
 import os
 
 import numpy as np
@@ -116,3 +117,42 @@ def test_oracle_sparse_gradients_vs_finite_differences(mode):
         assert abs(fd - g[p]) < 1e-4 * (1 + abs(fd)), (mode, p, fd, g[p])
     fdn = (orc.fitc_fit(mk(th), X, Xu, y, -1.0 + e, mode=mode)["mll"] - orc.fitc_fit(mk(th), X, Xu, y, -1.0 - e, mode=mode)["mll"]) / (2 * e)
     assert abs(fdn - f["dmll_noise"]) < 1e-4 * (1 + abs(fdn))
+
+
+def test_oracle_crossvalidation_matches_refits_and_finite_differences():
+    """Pins the oracle's restatement of src/crossvalidation.jl the way the reference's own test/test_crossvalidation.jl does:
+    analytic LOO / fold predictions == refitting without the held-out points; gradients == finite differences."""
+    rng = np.random.default_rng(1)
+    n = 24
+    x = np.sort(rng.uniform(-2, 2, n))[:, None]
+    y = np.abs(x[:, 0] - 5) * np.cos(2 * x[:, 0]) + 0.8 * rng.standard_normal(n)
+    spec, ln = ("SEIso", [0.5, 0.8]), math.log(0.8)
+    f = orc.fit(spec, x, y, ln)
+    mu, s2 = orc.predict_loo(f, y)
+    for i in (0, 7, 23):
+        keep = np.arange(n) != i
+        fi = orc.fit(spec, x[keep], y[keep], ln)
+        m, v = orc.predict_f(spec, x[keep], fi, x[i:i + 1])
+        assert abs(m[0] - mu[i]) < 1e-9 and abs(v[0] + math.exp(2 * ln) - s2[i]) < 1e-9
+    folds = [np.arange(0, 5), np.arange(5, 14), np.arange(14, 24)]
+    mus, Sigs = orc.predict_cvfold(f, y, folds)
+    V = folds[1]
+    keep = np.ones(n, bool); keep[V] = False
+    fV = orc.fit(spec, x[keep], y[keep], ln)
+    m, C = orc.predict_f(spec, x[keep], fV, x[V], full_cov=True)
+    assert np.allclose(m, mus[1], atol=1e-9) and np.allclose(C + math.exp(2 * ln) * np.eye(V.size), Sigs[1], atol=1e-9)
+
+    def crit(theta, lnn, which):
+        sp = ("SEIso", list(theta))
+        ff = orc.fit(sp, x, y, lnn)
+        return orc.logp_loo(ff, y) if which == "loo" else orc.logp_cvfold(ff, y, folds)
+
+    for which in ("loo", "fold"):
+        g = orc.dlogp_loo(spec, x, y, f, ln) if which == "loo" else orc.dlogp_cvfold(spec, x, y, f, ln, folds)
+        h = 1e-6
+        fd = [(crit([0.5, 0.8], ln + h, which) - crit([0.5, 0.8], ln - h, which)) / (2 * h)]
+        for p in range(2):
+            tp = [0.5, 0.8]; tm = [0.5, 0.8]
+            tp[p] += h; tm[p] -= h
+            fd.append((crit(tp, ln, which) - crit(tm, ln, which)) / (2 * h))
+        assert np.allclose(g, fd, rtol=1e-5, atol=1e-6), (which, g, fd)
