@@ -78,6 +78,7 @@ struct gpb200_handle {
     int dxp = 0;
     CUtensorMap mapX{}, mapXT{};
     bool xmap_ok = false;
+    int64_t capacity = 0;                      // option "capacity": rows reserved for gpb200_append (ElasticGPE's capacity)
     int gram_fast = 1;                         // option "gram_fast": 0 = always the generic kernels of gram.cu
     // cross-validation (gpb200_cv_*): K_y^-1 mirrored to a full symmetric matrix in G; two N x N temporaries
     bool g_sym = false;
@@ -1036,6 +1037,10 @@ int gpb200_create(gpb200_handle** out, int device) {
     if (env) h->gemm_impl = atoi(env);
     env = getenv("GPB200_DIST_NB");
     if (env) { int v = atoi(env); if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096) h->dist_nb = v; }
+    env = getenv("GPB200_SHARD_LA");
+    if (env) h->shard_la = atoi(env) ? 1 : 0;
+    env = getenv("GPB200_SHARD_RB");
+    if (env) { int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8) h->shard_rb_opt = v; }
     env = getenv("GPB200_NB");
     if (env) { int v = atoi(env); if (v == 0 || v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048 || v == 4096) h->nb = v; }
     *out = h;
@@ -1093,6 +1098,11 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "lookahead")) { h->lookahead = value ? 1 : 0; return GPB200_OK; }
     if (!strcmp(key, "gram_fast")) { h->gram_fast = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "leaf")) { potrf128_set_variant(value != 0); h->factored = h->inv_ready = false; return GPB200_OK; }
+    if (!strcmp(key, "capacity")) {             // rows reserved by the next gpb200_set_data (>= N): room for gpb200_append
+        if (value < 0 || value > ((int64_t)1 << 30)) return fail(h, GPB200_EINVAL, "capacity out of range");
+        h->capacity = value; return GPB200_OK;
+    }
     if (!strcmp(key, "shard")) {                // storage of F / G with several ranks: -1 auto, 0 replicated, 1 row-sharded
         if (value < -1 || value > 1) return fail(h, GPB200_EINVAL, "shard must be -1 (auto), 0 or 1");
         h->shard_opt = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
@@ -1144,7 +1154,7 @@ int gpb200_set_data(gpb200_handle* h, int64_t N, int32_t d, const double* x, int
     if (d > GPB200_MAX_DIMS) return fail(h, GPB200_EINVAL, "set_data: d exceeds GPB200_MAX_DIMS");
     if (N > (int64_t)1 << 30) return fail(h, GPB200_EINVAL, "set_data: N too large");
     CK(cudaSetDevice(h->device));
-    const int64_t Npad = (N + TILE - 1) / TILE * TILE;
+    const int64_t Npad = (std::max<int64_t>(N, h->capacity) + TILE - 1) / TILE * TILE;
     const bool realloc = !h->has_data || Npad != h->Npad || d != h->d;
     if (realloc) {
         free_data(h);
@@ -1643,6 +1653,77 @@ int gpb200_rand(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, con
     CK(add_rowvec_launch(h->rout, ldz, h->pmu, nsamp, M, h->st));                          // + mu (K*' alpha part)
     CK(cudaMemcpy2DAsync(samples, sizeof(double) * M, h->rout, sizeof(double) * ldz, sizeof(double) * M, nsamp, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    return GPB200_OK;
+}
+
+// ---- ElasticGPE append! (src/GPEelastic.jl:13-22): extend the factor by k new observations -----------------------------
+// The reference appends rows to an elastic Cholesky (ElasticPDMats.append!, a rank-k extension) and keeps the hyper-parameters
+// (update_target!(gp, kern=false, noise=false)).  Here the rows live inside the capacity reserved at set_data (option
+// "capacity"): only the block rows from the first touched 128-row tile on are rebuilt --
+//   Gram rows r >= c0;  L[r, 0:c0] = K[r, 0:c0] L11^-T (whitening TRSM against the existing factor);
+//   Schur complement of the trailing block (one GEMM with K = c0);  Cholesky of that small trailing block --
+// i.e. O(k N^2) instead of O(N^3).  Returns GPB200_EINVAL if N + k exceeds the capacity (the caller refits).
+int gpb200_append(gpb200_handle* h, int64_t k, const double* xnew, int64_t ldx) {
+    if (!h) return GPB200_EINVAL;
+    if (k <= 0 || !xnew || ldx < h->d) return fail(h, GPB200_EINVAL, "append: bad k, x or ldx");
+    if (!h->factored) return fail(h, GPB200_ESTATE, "append: factorize first");
+    if (h->nranks > 1) return fail(h, GPB200_ESTATE, "append: single-GPU handles only");
+    if (h->n_noise != 1) return fail(h, GPB200_ESTATE, "append: scalar logNoise only (per-point noise needs a refit)");
+    if (h->N + k > h->Npad) return fail(h, GPB200_EINVAL, "append: capacity exceeded (set option \"capacity\" before set_data, or refit)");
+    CK(cudaSetDevice(h->device));
+    const int64_t Nold = h->N, Nnew = Nold + k;
+    const int d = h->d, Np = (int)h->Npad;
+    const int c0 = (int)(Nold / TILE * TILE);                       // first tile row that changes
+    CK(cudaMemcpy2DAsync(h->x + Nold * d, sizeof(double) * d, xnew, sizeof(double) * ldx, sizeof(double) * d, k, cudaMemcpyHostToDevice, h->st));
+    h->xmap_ok = false;
+    if (h->xp) {
+        CK(cudaMemcpy2DAsync(h->xp + Nold * h->dxp, sizeof(double) * h->dxp, xnew, sizeof(double) * ldx, sizeof(double) * d, k, cudaMemcpyHostToDevice, h->st));
+        ++h->launches;
+        CK(shard_transpose(h->xpt, Np, h->xp, h->dxp, Np, h->dxp, h->st));
+        h->xmap_ok = gemm_make_tensor_map_plain(&h->mapX, h->xp, Nnew, h->dxp, h->dxp, TILE, h->dxp) &&
+                     gemm_make_tensor_map_plain(&h->mapXT, h->xpt, h->dxp, Nnew, Np, h->dxp, TILE);
+    }
+    h->N = Nnew;
+    h->inv_ready = h->alpha_ready = false; h->g_sym = false;
+    const int init = INT_MAX;
+    CK(cudaMemcpyAsync(h->info_dev, &init, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    ++h->launches;
+    // Gram rows >= c0 (columns <= row), identity beyond the new N
+    CK(gram_lower_launch(h->prog, h->x, d, d, Nnew, Np, h->noise_var, 1, h->nugget, h->G, h->ld, h->st, 0, 1, 0, 0, c0 / TILE));
+    cudaError_t e = cudaSuccess;
+    if (c0 > 0) {
+        // rows >= c0 of G against the existing factor: G[r, 0:c0] <- G[r, 0:c0] L11^-T, then keep them as rows of L
+        CUtensorMap sub{};
+        double* gsub = h->G + (size_t)c0 * h->ld;
+        const bool tma = h->tma_ok && gemm_make_tensor_map(&sub, gsub, Np - c0, Np, h->ld);
+        GemmBuf bk{tma ? &sub : nullptr, gsub, h->ld};
+        const int impl_save = h->gemm_impl;
+        if (!tma) h->gemm_impl = 1;
+        e = trsm_rec_buf(h, bk, Np - c0, 0, c0);
+        h->gemm_impl = impl_save;
+        CK(e);
+        CK(cudaMemcpy2DAsync(h->F + (size_t)c0 * h->ld, sizeof(double) * h->ld, gsub, sizeof(double) * h->ld, sizeof(double) * c0, Np - c0,
+                             cudaMemcpyDeviceToDevice, h->st));
+        // Schur complement of the trailing block:  G[r, c] -= sum_{k < c0} L[r, k] L[c, k],  r >= c >= c0
+        CK(schur_update(h, c0, Np - c0, Np - c0, 0, c0));
+    }
+    // factor the trailing block tile by tile (right-looking, 128-wide panels)
+    for (int p = c0; p < Np; p += TILE) {
+        CK(chol_panel(h, p, TILE, TILE));
+        const int rem = Np - p - TILE;
+        if (rem > 0) CK(schur_update(h, p + TILE, rem, rem, p, TILE));
+    }
+    int info = 0;
+    CK(cudaMemcpyAsync(&info, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    profile_collect(h);
+    if (info != INT_MAX) {
+        h->factored = false;
+        char buf[128];
+        snprintf(buf, sizeof buf, "append: extended matrix is not positive definite; leading minor %d", info);
+        h->err = buf;
+        return info > h->N ? (int)h->N : info;
+    }
     return GPB200_OK;
 }
 

@@ -38,9 +38,9 @@ __global__ void __launch_bounds__(NT) gram_lower_kernel(const __grid_constant__ 
                                                         long long ldx, int d, long long N, long long Npad,
                                                         const double* __restrict__ noise_var, long long n_noise,
                                                         double nugget, double* __restrict__ G, long long ldg,
-                                                        int own_tiles, int nranks, int rank, int own_axis) {
+                                                        int own_tiles, int nranks, int rank, int own_axis, int bm_min) {
     const int bm = blockIdx.y, bn = blockIdx.x;
-    if (bn > bm) return;
+    if (bn > bm || bm < bm_min) return;
     // multi-GPU ownership: block columns (replicated storage, own_axis 0) or block rows (row-sharded storage, own_axis 1)
     if (own_tiles > 0 && (((own_axis ? bm : bn) / own_tiles) % nranks) != rank) return;
     extern __shared__ double sm[];
@@ -466,17 +466,17 @@ cudaError_t ensure_smem(K kern, size_t bytes) {
 
 cudaError_t gram_lower_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad,
                               const double* noise_var, int64_t n_noise, double nugget, double* G, int64_t ldg,
-                              cudaStream_t st, int own_tiles, int nranks, int rank, int own_axis) {
+                              cudaStream_t st, int own_tiles, int nranks, int rank, int own_axis, int bm_min) {
     const int T = (int)(Npad / TB);
     dim3 grid(T, T);
     const size_t sm = xtile_smem(d);
     cudaError_t e;
     if (P.fast) {
         if ((e = ensure_smem(gram_lower_kernel<true>, sm)) != cudaSuccess) return e;
-        gram_lower_kernel<true><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis);
+        gram_lower_kernel<true><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis, bm_min);
     } else {
         if ((e = ensure_smem(gram_lower_kernel<false>, sm)) != cudaSuccess) return e;
-        gram_lower_kernel<false><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis);
+        gram_lower_kernel<false><<<grid, NT, sm, st>>>(P, x, ldx, d, N, Npad, noise_var, n_noise, nugget, G, ldg, own_tiles, nranks, rank, own_axis, bm_min);
     }
     return cudaGetLastError();
 }

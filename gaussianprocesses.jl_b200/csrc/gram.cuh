@@ -7,7 +7,7 @@
 // lower tiles of K_y (+ noise on the diagonal, identity in the padding) into G (row-major, ld = ldg)
 cudaError_t gram_lower_launch(const KProg& P, const double* x, int64_t ldx, int d, int64_t N, int64_t Npad,
                               const double* noise_var, int64_t n_noise, double nugget, double* G, int64_t ldg,
-                              cudaStream_t st, int own_tiles = 0, int nranks = 1, int rank = 0, int own_axis = 0);
+                              cudaStream_t st, int own_tiles = 0, int nranks = 1, int rank = 0, int own_axis = 0, int bm_min = 0);
 // Kst[m, n] = k(xs_m, x_n), M_pad x N_pad, zero padding
 cudaError_t crossgram_launch(const KProg& P, const double* xs, int64_t ldxs, int64_t M, int64_t Mpad, const double* x,
                              int64_t ldx, int64_t N, int64_t Npad, int d, double* Kst, int64_t ldk, cudaStream_t st);

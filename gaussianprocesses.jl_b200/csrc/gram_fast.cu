@@ -10,11 +10,12 @@
 // differences summed in dimension order, as src/kernels/distance.jl:43-56.
 //
 // Why a hand-written exp: the kernel is bound by the FP64 pipe, not by HBM (d = 8: 16 FP64 ops for the distance;
-// CUDA's exp() adds ~30 more).  exp(x) = 2^z, z = x log2(e), is evaluated as  T[k mod 32] * p(f) * 2^(k div 32)  with
-// k = round(32 z), f = z - k/32 (|f| <= 1/64), p = degree-6 Taylor polynomial of 2^f (truncation 3.5e-18), T[j] =
-// sigma^2 2^(j/32) rounded once on the host, and the power of two applied by an integer add to the exponent field:
-// 9 FP64 instructions, < 2 ulp.  The argument uses a two-word constant (c_hi + c_lo) so that no rounding beyond r's own
-// enters the exponent.  ~27 FP64 instructions per output instead of ~46.
+// CUDA's exp() adds ~30 more).  exp(x) = 2^z, z = r * c, c = -log2(e) / (2 l^2), is evaluated as
+// T[k mod 64] * p(f) * 2^(k div 64)  with k = round(64 z), f = z - k/64 (|f| <= 1/128), p = degree-5 Taylor polynomial of 2^f
+// (truncation 3.5e-17), T[j] = sigma^2 2^(j/64) rounded once on the host, the power of two applied by an integer add to the
+// exponent field and underflow detected in the integer pipe: 9 FP64 instructions including the argument, < 2 ulp of the
+// exponential of the rounded argument (the argument's own rounding, |x| eps relative, is what any exp(-r/2l^2) carries).
+// 25 FP64 instructions per output instead of ~46: 1.19 ms -> ... at C2 (profiles/).
 #include "gram_fast.cuh"
 #include <math.h>
 #include <stdint.h>
@@ -44,26 +45,28 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                  : "memory");
 }
 
-// sigma^2 * 2^z for z <= 0 (clamped at -960: values below 1e-289 sigma^2 are returned as ~1e-289 sigma^2).
-// The 32-entry table is replicated 16 times in shared memory, entry j of copy c at word j*16 + c, and lane l reads copy
-// l % 16: the 16 lanes of a half-warp always hit 16 different bank pairs, whatever their indices (the plain 32-entry table
-// cost ~9 extra LSU cycles per lookup in bank conflicts: ncu l1tex__data_bank_conflicts 154 M per launch at C2).
+// sigma^2 * 2^z for z <= 0; exactly 0 below z = -960 (true values < 1e-289 sigma^2).
+// 2^z = T[k mod 64] * p(f) * 2^(k div 64), k = round(64 z), f = z - k/64 (|f| <= 1/128), p = degree-5 Taylor polynomial of
+// 2^f (truncation 3.5e-17); 8 FP64 instructions.  The 64-entry table is replicated 16 times in shared memory, entry j of copy
+// c at word j*16 + c, and lane l reads copy l % 16: the 16 lanes of a half-warp always hit 16 different bank pairs, whatever
+// their indices (a plain table cost ~9 extra LSU cycles per lookup: ncu l1tex__data_bank_conflicts 154 M per launch at C2).
+constexpr int TABN = 64;
 __device__ __forceinline__ double exp2_tab(double z, const double* __restrict__ tab) {
-    z = fmax(z, -960.0);
-    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: the low mantissa bits hold round(32 z)
-    const double zs = fma(z, 32.0, MAGIC);
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: the low mantissa bits hold round(64 z)
+    const double zs = fma(z, 64.0, MAGIC);
     const int ki = __double2loint(zs);
     const double kf = zs - MAGIC;
-    const double f = fma(kf, -0.03125, z);                    // exact
-    double p = 1.5403530393381609954e-4;                      // ln2^6 / 720
-    p = fma(p, f, 1.3333558146428443423e-3);                  // ln2^5 / 120
+    const double f = fma(kf, -0.015625, z);                   // exact
+    double p = 1.3333558146428443423e-3;                      // ln2^5 / 120
     p = fma(p, f, 9.6181291076284771619e-3);                  // ln2^4 / 24
     p = fma(p, f, 5.5504108664821579953e-2);                  // ln2^3 / 6
     p = fma(p, f, 2.4022650695910071233e-1);                  // ln2^2 / 2
     p = fma(p, f, 6.9314718055994530942e-1);                  // ln2
     p = fma(p, f, 1.0);
-    const double r = tab[(ki & 31) << 4] * p;                 // tab already points at this lane's copy (bank pair lane % 16)
-    return __hiloint2double(__double2hiint(r) + ((ki >> 5) << 20), __double2loint(r));
+    const double r = tab[(ki & (TABN - 1)) << 4] * p;         // tab already points at this lane's copy (bank pair lane % 16)
+    const double v = __hiloint2double(__double2hiint(r) + ((ki >> 6) << 20), __double2loint(r));
+    // underflow guard in the integer pipe: z <= -960 (high word compare; z <= 0 always) -> 0, whatever k wrapped to
+    return ((unsigned)__double2hiint(z) > 0xC08E0000u) ? 0.0 : v;
 }
 
 __device__ __forceinline__ void tri_decode(int lin, int& bm, int& bn) {
@@ -103,12 +106,12 @@ gram_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                       long long ldg, int own_tiles, int nranks, int rank, int own_axis) {
     __shared__ __align__(128) double sXi[TB * DX];
     __shared__ __align__(128) double sXj[TB * DX];
-    __shared__ double sTabR[32 * 16];
+    __shared__ double sTabR[TABN * 16];
     __shared__ __align__(8) uint64_t bar;
     int bm, bn;
     tri_decode(blockIdx.x, bm, bn);
     if (own_tiles > 0 && (((own_axis ? bm : bn) / own_tiles) % nranks) != rank) return;
-    for (int i = threadIdx.x; i < 32 * 16; i += NT) sTabR[i] = sf.tab[i >> 4];
+    for (int i = threadIdx.x; i < TABN * 16; i += NT) sTabR[i] = sf.tab[i >> 4];
     const double* sTab = sTabR + (threadIdx.x & 15);
     const bool finite = stage_tiles<DX>(&mapX, &mapXT, sXi, sXj, &bar, bm, bn);
 
@@ -121,7 +124,7 @@ gram_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         xj[0][k] = lo.x; xj[1][k] = lo.y; xj[2][k] = hi.x; xj[3][k] = hi.y;
     }
     const bool plain = finite && (bm != bn) && ((long long)(bm + 1) * TB <= N);
-    const double c_hi = sf.c_hi, c_lo = sf.c_lo;
+    const double c_hi = sf.c_hi;
     double* gbase = G + ((long long)bm * TB + warp * 16) * ldg + (long long)bn * TB + lane * 2;
     if (plain) {
 #pragma unroll 2
@@ -136,7 +139,7 @@ gram_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 double r2 = 0.0;
 #pragma unroll
                 for (int k = 0; k < DX; ++k) { const double df = xir[k] - xj[q][k]; r2 = fma(df, df, r2); }
-                v[q] = exp2_tab(fma(r2, c_hi, r2 * c_lo), sTab);
+                v[q] = exp2_tab(r2 * c_hi, sTab);
             }
             double* row = gbase + (long long)rr * ldg;
             *reinterpret_cast<double2*>(row) = make_double2(v[0], v[1]);
@@ -157,7 +160,7 @@ gram_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             double r2 = 0.0;
 #pragma unroll
             for (int k = 0; k < DX; ++k) { const double df = xi[k] - xj[q][k]; r2 = fma(df, df, r2); }
-            double kv = finite ? exp2_tab(fma(r2, c_hi, r2 * c_lo), sTab) : sf.s2 * exp(-0.5 * r2 * sf.il2);
+            double kv = finite ? exp2_tab(r2 * c_hi, sTab) : sf.s2 * exp(-0.5 * r2 * sf.il2);
             if (gi >= N || gj >= N) kv = (gi == gj) ? 1.0 : 0.0;
             else if (gi == gj) kv += ((n_noise == 1) ? noise_var[0] : noise_var[gi]) + nugget;
             v[q] = kv;
@@ -178,8 +181,9 @@ trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
                        double* __restrict__ part, int bm_mod, int bm_rem, int bm_div) {
     __shared__ __align__(128) double sXi[TB * DX];
     __shared__ __align__(128) double sXj[TB * DX];
-    __shared__ double sTabR[32 * 16];
-    __shared__ double sAi[TB], sAj[TB];
+    __shared__ double sTabR[TABN * 16];
+    __shared__ __align__(16) double sAi[TB];
+    __shared__ __align__(16) double sAj[TB];
     __shared__ double sRed[8 * 3];
     __shared__ __align__(8) uint64_t bar;
     int bm, bn;
@@ -189,7 +193,7 @@ trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
         if (threadIdx.x < 3) part[lin * 3 + threadIdx.x] = 0.0;
         return;
     }
-    for (int i = threadIdx.x; i < 32 * 16; i += NT) sTabR[i] = sf.tab[i >> 4];
+    for (int i = threadIdx.x; i < TABN * 16; i += NT) sTabR[i] = sf.tab[i >> 4];
     const double* sTab = sTabR + (threadIdx.x & 15);
     if (threadIdx.x < TB) {
         const long long gi = (long long)bm * TB + threadIdx.x, gj = (long long)bn * TB + threadIdx.x;
@@ -209,10 +213,18 @@ trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
         xj[0][k] = lo.x; xj[1][k] = lo.y; xj[2][k] = hi.x; xj[3][k] = hi.y;
     }
     const bool plain = finite && (bm != bn) && ((long long)(bm + 1) * TB <= N);
-    const double c_hi = sf.c_hi, c_lo = sf.c_lo;
+    const double c_hi = sf.c_hi;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     const double* kbase = Kinv + ((long long)bm * TB + warp * 16) * ldg + (long long)bn * TB + lane * 2;
     if (plain) {
+        // the K^-1 values of a row are fetched two rows ahead (register double-buffer): the global-load latency (~1.5k cycles)
+        // is covered by two rows of FP64 work instead of stalling every row (ncu: FP64 pipe 42% -> with the plain loop)
+        double2 pa[2], pb[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            pa[s] = *reinterpret_cast<const double2*>(kbase + (long long)s * ldg);
+            pb[s] = *reinterpret_cast<const double2*>(kbase + (long long)s * ldg + 64);
+        }
 #pragma unroll 2
         for (int rr = 0; rr < 16; ++rr) {
             const int r = warp * 16 + rr;
@@ -221,16 +233,22 @@ trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
 #pragma unroll
             for (int k = 0; k < DX / 2; ++k) { const double2 t2 = xi2[k]; xir[2 * k] = t2.x; xir[2 * k + 1] = t2.y; }
             const double ai = sAi[r];
-            const double2 k01 = *reinterpret_cast<const double2*>(kbase + (long long)rr * ldg);
-            const double2 k23 = *reinterpret_cast<const double2*>(kbase + (long long)rr * ldg + 64);
+            const double2 k01 = pa[rr & 1], k23 = pb[rr & 1];
+            if (rr + 2 < 16) {
+                pa[rr & 1] = *reinterpret_cast<const double2*>(kbase + (long long)(rr + 2) * ldg);
+                pb[rr & 1] = *reinterpret_cast<const double2*>(kbase + (long long)(rr + 2) * ldg + 64);
+            }
             const double kin[4] = {k01.x, k01.y, k23.x, k23.y};
+            const double2 a01 = *reinterpret_cast<const double2*>(sAj + lane * 2);        // re-read per row: frees 8 registers
+            const double2 a23 = *reinterpret_cast<const double2*>(sAj + 64 + lane * 2);
+            const double ajr[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 double r2 = 0.0;
 #pragma unroll
                 for (int k = 0; k < DX; ++k) { const double df = xir[k] - xj[q][k]; r2 = fma(df, df, r2); }
-                const double kv = exp2_tab(fma(r2, c_hi, r2 * c_lo), sTab);
-                const double t = fma(ai, aj[q], -kin[q]) * kv;                 // A k
+                const double kv = exp2_tab(r2 * c_hi, sTab);
+                const double t = fma(ai, ajr[q], -kin[q]) * kv;                // A k
                 acc0 = fma(t, r2, acc0);                                       // * 1/l^2 at the end
                 acc1 += t;                                                     // * 2 at the end
             }
@@ -251,7 +269,7 @@ trace_seiso_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
                 double r2 = 0.0;
 #pragma unroll
                 for (int k = 0; k < DX; ++k) { const double df = xi[k] - xj[q][k]; r2 = fma(df, df, r2); }
-                const double kv = finite ? exp2_tab(fma(r2, c_hi, r2 * c_lo), sTab) : sf.s2 * exp(-0.5 * r2 * sf.il2);
+                const double kv = finite ? exp2_tab(r2 * c_hi, sTab) : sf.s2 * exp(-0.5 * r2 * sf.il2);
                 const double A = fma(ai, aj[q], -kinv);
                 const double t = ((gi == gj) ? 0.5 * A : A) * kv;
                 acc0 = fma(t, r2, acc0);
@@ -302,7 +320,7 @@ bool seiso_fast_prepare(double l2, double s2, SeIsoFast* out) {
     out->c_lo = (double)(c - (long double)out->c_hi);
     out->il2 = 1.0 / l2;
     out->s2 = s2;
-    for (int j = 0; j < 32; ++j) out->tab[j] = (double)((long double)s2 * exp2l((long double)j / 32.0L));
+    for (int j = 0; j < 64; ++j) out->tab[j] = (double)((long double)s2 * exp2l((long double)j / 64.0L));
     return true;
 }
 

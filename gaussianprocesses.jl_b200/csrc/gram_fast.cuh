@@ -8,7 +8,7 @@
 struct SeIsoFast {
     double c_hi, c_lo;
     double il2, s2;
-    double tab[32];                 // s2 * 2^(j/32), correctly rounded
+    double tab[64];                 // s2 * 2^(j/64), correctly rounded
 };
 // false if (l2, s2) lie outside the range in which the exponent arithmetic of the fast exp is safe
 bool seiso_fast_prepare(double l2, double s2, SeIsoFast* out);

@@ -385,6 +385,7 @@ int ensure_storage(gpb200_handle* h) {
     const bool ok_now = h->F && h->G && h->sharded == want && (!want || h->rb == shard_pick_rb(h));
     if (ok_now) return GPB200_OK;
     CK(cudaStreamSynchronize(h->st));
+    close_peer_maps(h);                                       // peers' IPC views of the old buffers die with them (every rank re-allocates)
     if (h->F || h->G) free_FG(h);
     return want ? alloc_FG_sharded(h) : alloc_FG_replicated(h);
 }

@@ -5,6 +5,6 @@ from .kernels import (Kernel, SEIso, SEArd, SE, Mat12Iso, Mat32Iso, Mat52Iso, Ma
                       RQIso, RQArd, RQ, Periodic, LinIso, LinArd, Poly, Noise, Const, SumKernel, ProdKernel, Masked,
                       FixedKernel, fix, flatten)
 from .means import Mean, MeanZero, MeanConst, MeanLin
-from .gpe import GPE, GP
+from .gpe import GPE, GP, ElasticGPE
 from .sparse import FITC, DTC, SoR
 from . import dist

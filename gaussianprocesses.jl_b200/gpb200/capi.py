@@ -38,6 +38,7 @@ _SIGNATURES = {
     "gpb200_grad_kernel": (C.c_int, [_H, _dp, _dp, _dp]),
     "gpb200_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp]),
     "gpb200_rand": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp, C.c_double, _dp, _dp]),
+    "gpb200_append": (C.c_int, [_H, C.c_int64, _dp, C.c_int64]),
     "gpb200_cv_param": (C.c_int, [_H, C.c_int32, _dp, _dp, _dp]),
     "gpb200_cv_block": (C.c_int, [_H, C.c_int32, C.c_int64, C.POINTER(C.c_int64), _dp]),
     "gpb200_get_gram": (C.c_int, [_H, _dp]),
@@ -231,6 +232,15 @@ class Engine:
         self._check(self._lib.gpb200_rand(self._h, M, _as_dp(xs_pm), d, ap, z.shape[0], _as_dp(z), float(nugget), _as_dp(mu),
                                           _as_dp(out)), "rand")
         return mu, out
+
+    def append(self, xnew_pm):
+        """extend the factor by the rows of xnew_pm (k, d) with unchanged hyper-parameters (ElasticGPE append!)"""
+        xnew_pm = np.ascontiguousarray(xnew_pm, dtype=np.float64)
+        k, d = xnew_pm.shape
+        if d != self.d:
+            raise ValueError("append: wrong input dimension")
+        self._check(self._lib.gpb200_append(self._h, k, _as_dp(xnew_pm), d), "append")
+        self.N += k
 
     def cv_param(self, param, alpha=None):
         """(Z_j alpha, diag(Z_j K^-1)) for kernel parameter `param` (index into the full parameter vector) or -1 = noise."""

@@ -31,7 +31,7 @@ class _RejectedStep(Exception):
 
 
 class GPE:
-    def __init__(self, x, y, mean=None, kernel=None, logNoise=-2.0, device=0, engine=None):
+    def __init__(self, x, y, mean=None, kernel=None, logNoise=-2.0, device=0, engine=None, capacity=0, stepsize=1000):
         if kernel is None or not isinstance(kernel, Kernel):
             raise ValueError("GPE needs a kernel")
         self.mean = mean if mean is not None else MeanZero()
@@ -40,6 +40,9 @@ class GPE:
         self.kernel = kernel
         self.logNoise = float(logNoise) if np.ndim(logNoise) == 0 else np.asarray(logNoise, dtype=np.float64).copy()
         self._eng = engine if engine is not None else capi.Engine(device)
+        self._capacity, self._stepsize = int(capacity), int(stepsize)       # ElasticGPE(...; capacity, stepsize), GPEelastic.jl:55-66
+        if self._capacity:
+            self._eng.set_option("capacity", self._capacity)
         self.alpha = None
         self.mll = float("nan")
         self.target = float("nan")
@@ -74,6 +77,28 @@ class GPE:
             raise ValueError("Input observations must have the same dimension as the GP")
         y = np.atleast_1d(np.asarray(y, dtype=np.float64)).ravel()
         return self.fit(np.concatenate([self.x, x], axis=1), np.concatenate([self.y, y]))
+
+    def append(self, x, y):
+        """append!(gp::ElasticGPE, x, y) (src/GPEelastic.jl:13-22): add observations keeping the hyper-parameters; the device
+        extends its Cholesky factor in place (O(k N^2)) and update_target!(gp, kern=false, noise=false) refreshes alpha / mll.
+        Needs a GPE built with `capacity=` (ElasticGPE(...; capacity, stepsize)); beyond the capacity the data is refitted with
+        `stepsize` more rows reserved, which is what ElasticPDMats' resize! amounts to."""
+        x = _as_dxn(x)
+        if x.shape[0] != self.dim:
+            raise ValueError("Input observations must have the same dimension as the GP")
+        y = np.atleast_1d(np.asarray(y, dtype=np.float64)).ravel()
+        if x.shape[1] != y.size:
+            raise ValueError("%d observations, but %d targets." % (x.shape[1], y.size))        # GPEelastic.jl:15
+        if np.ndim(self.logNoise) or self.nobs + y.size > getattr(self, "_capacity", 0):
+            self._capacity = self.nobs + y.size + getattr(self, "_stepsize", 1000)
+            self._eng.set_option("capacity", self._capacity)
+            return self.fit(np.concatenate([self.x, x], axis=1), np.concatenate([self.y, y]))
+        self._eng.append(np.ascontiguousarray(x.T))
+        self.x = np.concatenate([self.x, x], axis=1)
+        self.y = np.concatenate([self.y, y])
+        self.nobs = self.y.size
+        self._xpm = np.ascontiguousarray(self.x.T)
+        return self.update_target(kern=False, noise=False)                                  # GPEelastic.jl:21
 
     def reload_data(self, x, y):
         """Re-upload (x, y) of unchanged shape to the device without re-evaluating the target
@@ -352,3 +377,9 @@ class GPE:
 
 def GP(x, y, mean, kernel, logNoise=-2.0, **kw):                   # GPE.jl:119
     return GPE(x, y, mean, kernel, logNoise, **kw)
+
+
+def ElasticGPE(x, y, mean=None, kernel=None, logNoise=-2.0, capacity=1000, stepsize=1000, **kw):
+    """ElasticGPE(x, y, mean, kernel, logNoise; capacity, stepsize) (src/GPEelastic.jl:55-66): a GPE whose device buffers
+    reserve `capacity` observations so that append! extends the factor in place."""
+    return GPE(x, y, mean, kernel, logNoise, capacity=max(int(capacity), np.asarray(y).size), stepsize=stepsize, **kw)

@@ -130,6 +130,12 @@ int  gpb200_predict(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs,
 int  gpb200_rand(gpb200_handle* h, int64_t M, const double* xs, int64_t ldxs, const double* alpha, int64_t nsamp,
                  const double* z, double nugget, double* mu_minus_mean, double* samples);
 
+/* append!(gp::ElasticGPE, x, y) (src/GPEelastic.jl:13-22): k more observations (xnew: d x k column-major) with UNCHANGED
+ * hyper-parameters; the factor is extended in place (rows from the first touched tile on are rebuilt: O(k N^2)), alpha / mll are
+ * then refreshed with gpb200_mll on the longer y.  Needs room reserved by option "capacity" (ElasticGPE's capacity) before
+ * gpb200_set_data; GPB200_EINVAL when the capacity is exceeded (the shim refits, like ElasticPDMats.resize!).             */
+int  gpb200_append(gpb200_handle* h, int64_t k, const double* xnew, int64_t ldx);
+
 /* ---- cross-validation on the resident inverse (src/crossvalidation.jl; after gpb200_grad_prepare, single GPU) ------------
  * Per hyper-parameter the reference forms Z_j = inv(Sigma) dK_j and Z_j inv(Sigma) as host matrices (crossvalidation.jl:86-108,
  * 270-283).  gpb200_cv_param does the two N^3 products on the device and returns the two vectors the LOO formulas need:
@@ -165,6 +171,9 @@ int64_t gpb200_launch_count(gpb200_handle* h);
  *   "p2p"        multi-GPU: 1 = fused panel push over peer memory (after gpb200_ipc_import), 0 = NCCL broadcast
  *   "gram_fast"  1 (default) = TMA-staged SEIso Gram / trace kernels (gram_fast.cu) when the kernel is one SEIso leaf over
  *                <= 8 dimensions, 0 = always the generic kernel-program kernels (cross-check)
+ *   "leaf"       1 (default) = blocked 128 x 128 diagonal-tile kernel (16-column panels), 0 = column-per-barrier kernel
+ *                (cross-check; process-wide)
+ *   "capacity"   rows reserved by the next gpb200_set_data (>= N) so that gpb200_append can extend the factor in place
  *   "shard"      multi-GPU storage of the two N x N buffers: 1 = row-sharded (each rank maps only its own block rows),
  *                0 = replicated, -1 (default) = sharded only when the replicated form would not fit the device
  *   "shard_la"   1 (default) = look-ahead schedules of the row-sharded Cholesky / inverse (panel chain on a side stream),

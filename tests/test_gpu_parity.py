@@ -386,3 +386,67 @@ def test_crossvalidation_on_device_matches_oracle(engine):
     gp.update_dmll()
     o = orc.mll_and_dmll(k.spec(), X, y, ln)
     assert np.allclose(gp.dmll, o["dmll"], rtol=1e-8, atol=1e-10)
+
+
+def test_elastic_append_matches_batch_fit():
+    """ElasticGPE append! (src/GPEelastic.jl:13-22; test/elastic.jl:17-29: incremental == batch Cholesky / alpha / mll): the
+    device extends its factor in place inside the reserved capacity; beyond it the host mirror refits with more room."""
+    import gpb200
+    X, y, Xs = make_data(1000, 2, 23, m=40)
+    k = gpb200.Mat32Iso(0.3, 0.1) + gpb200.SEIso(0.6, -0.3)
+    gp = gpb200.ElasticGPE(X[:300].T, y[:300], gpb200.MeanConst(0.1), k, -0.8, capacity=700, stepsize=200)
+    n = 300
+    for step in (1, 50, 200, 100, 260):                      # within a tile, across tiles, up to the capacity, beyond it (refit)
+        l0 = gp._eng.launch_count()
+        gp.append(X[n:n + step].T, y[n:n + step])
+        n += step
+        assert gp.nobs == n and gp.alpha.size == n
+        o = orc.fit(k.spec(), X[:n], y[:n], -0.8, ("MeanConst", 0.1))
+        assert abs(gp.mll - o["mll"]) <= 1e-10 * abs(o["mll"]), (step, gp.mll, o["mll"])
+        assert _rel(gp.alpha, o["alpha"]) < 1e-10
+        mu, s2 = gp.predict_f(Xs.T)
+        mo, vo = orc.predict_f(k.spec(), X[:n], o, Xs, ("MeanConst", 0.1))
+        assert _rel(mu, mo) < 1e-10 and np.max(np.abs(s2 - vo)) <= 1e-10 * np.max(np.abs(vo)) + 1e-13
+    # the gradient path works on the extended factor
+    gp.update_dmll()
+    og = orc.mll_and_dmll(k.spec(), X[:n], y[:n], -0.8, ("MeanConst", 0.1))
+    assert np.allclose(gp.dmll, og["dmll"], rtol=1e-8, atol=1e-10)
+    with pytest.raises(ValueError):
+        gp.append(np.zeros((3, 2)), [0.0, 1.0])
+
+
+def test_blocked_diagonal_tile_kernel_matches_column_kernel(engine):
+    """potrf_base.cu: the blocked 128 x 128 leaf (16-column panels, option "leaf" = 1) against the column-per-barrier leaf and
+    the oracle: factor, inverted tiles (through solve / K^-1), log-determinant, and the not-positive-definite report."""
+    import gpb200
+    X, y, _ = make_data(1000, 3, 41)
+    k = gpb200.Mat52Iso(0.0, 0.2) + gpb200.SEIso(0.4, -0.1)
+    theta, _ = _setup(engine, k, X, nb=0, gemm=0)
+    o = orc.fit(k.spec(), X, y, -1.2)
+    out = {}
+    for leaf in (0, 1):
+        engine.set_option("leaf", leaf)
+        engine.factorize(theta, -1.2)
+        U = engine.factor_upper()
+        alpha, mll = engine.mll(y)
+        engine.grad_prepare()
+        out[leaf] = (U, alpha, mll, engine.logdet(), engine.inverse())
+    engine.set_option("leaf", 1)
+    Ky = orc.gram(k.spec(), X, -1.2)
+    for leaf in (0, 1):
+        U, alpha, mll, ld, Kinv = out[leaf]
+        assert np.max(np.abs(U.T @ U - Ky)) <= 1e-12 * np.max(np.abs(Ky))
+        assert abs(mll - o["mll"]) <= RTOL * abs(o["mll"]) and _rel(alpha, o["alpha"]) < RTOL
+        assert abs(ld - np.linalg.slogdet(Ky)[1]) <= 1e-11 * abs(ld)
+        assert np.max(np.abs(Kinv @ Ky - np.eye(1000))) <= 1e-9
+    assert _rel(out[1][0], out[0][0]) < 1e-12
+    # non-PD: reported by both kernels
+    Xd = X.copy(); Xd[700] = Xd[3]
+    engine.set_data(Xd)
+    for leaf in (0, 1):
+        engine.set_option("leaf", leaf)
+        with pytest.raises(gpb200.PosDefException) as ei:
+            engine.factorize(theta, -40.0)
+        out[leaf] = ei.value.info
+    engine.set_option("leaf", 1)
+    assert out[0] >= 1 and out[1] >= 1          # both report a failing leading minor (its index depends on the pivot's rounding)
