@@ -186,6 +186,11 @@ struct gpb200_fitc {
     CUtensorMap mapAt{}, mapC{}, mapCt{}, mapH{}, mapT{};
     bool grad_ws = false;
     double* Kss = nullptr; int64_t Kss_rows = 0;      // full predictive covariance (gpb200_fitc_predict_cov)
+    // multi-GPU (gpb200_fitc_comm_init): the N observations are sharded over the ranks, every M x M object is replicated;
+    // exchanged: one all-reduce of the M x M accumulator Sigma_QR (and of H for the kernel gradient), M-vectors, scalars
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    double Ntotal = 0.0;                              // observations over all ranks (mll's N log 2 pi)
     int mode = 0;                    // 0 FITC, 1 DTC, 2 SoR (Lambda = sigma^2 I; SoR also drops K_xx - Q_xx from the predictive variance)
     double noise_var = 0.0;
     bool has_data = false, has_kernel = false, factored = false, alpha_ready = false;
@@ -2052,6 +2057,34 @@ int gpb200_group_create(gpb200_handle** hs, int n) {
         if (rc_ != GPB200_OK) { f->err = std::string(#call) + ": " + (who)->err; return rc_; }     \
     } while (0)
 
+#define FCKN(call)                                                                                 \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            f->err = std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); \
+            return GPB200_ENCCL;                                                                   \
+        }                                                                                          \
+    } while (0)
+// in-place sum over the ranks of a device vector (no-op on one rank)
+static int fitc_allreduce(gpb200_fitc* f, double* v, size_t n) {
+    if (f->nranks <= 1 || n == 0) return GPB200_OK;
+    FCKN(g_nccl.AllReduce(v, v, n, ncclDouble, ncclSum, f->comm, f->eu->st));
+    return GPB200_OK;
+}
+
+int gpb200_fitc_comm_init(gpb200_fitc* f, int nranks, int rank, const char* id128) {
+    if (!f || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return GPB200_EINVAL;
+    if (!nccl_load()) { f->err = "libnccl.so.2 could not be loaded"; return GPB200_ENCCL; }
+    FCK(cudaSetDevice(f->device));
+    if (f->comm) { g_nccl.CommDestroy(f->comm); f->comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    FCKN(g_nccl.CommInitRank(&f->comm, nranks, id, rank));
+    f->nranks = nranks; f->rank = rank;
+    f->factored = f->alpha_ready = false;
+    return GPB200_OK;
+}
+
 void gpb200_fitc_destroy(gpb200_fitc* f) {
     if (!f) return;
     cudaSetDevice(f->device);
@@ -2061,6 +2094,7 @@ void gpb200_fitc_destroy(gpb200_fitc* f) {
                        &f->bufC, &f->Hbuf, &f->Wbuf, &f->Tbuf, &f->gvec, &f->betav, &f->gpart, &f->gacc, &f->gtmp};
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (f->Kss) cudaFree(f->Kss);
+    if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(f->comm);
     if (f->es) { f->es->st = nullptr; f->es->own_stream = false; gpb200_destroy(f->es); }
     if (f->eu) gpb200_destroy(f->eu);
     delete f;
@@ -2163,7 +2197,8 @@ int gpb200_fitc_factorize(gpb200_fitc* f, const double* theta, double log_noise)
     FCK(cudaMemcpyAsync(es->noise_var, &zero, sizeof(double), cudaMemcpyHostToDevice, st));
     es->n_noise = 1; es->nugget = 2e-10;
     ++es->launches;
-    FCK(gram_lower_launch(es->prog, es->x, f->d, f->d, f->M, f->Mpad, es->noise_var, 1, 2e-10, es->G, es->ld, st));
+    if (f->rank == 0) FCK(gram_lower_launch(es->prog, es->x, f->d, f->d, f->M, f->Mpad, es->noise_var, 1, 2e-10, es->G, es->ld, st));
+    else FCK(cudaMemsetAsync(es->G, 0, sizeof(double) * (size_t)f->Mpad * (size_t)f->Mpad, st));     // K_uu (+ nuggets, identity padding) enters the sum once
     f->noise_var = exp(2.0 * log_noise);
     GemmBuf bA{eu->tma_ok ? &f->mapA : nullptr, f->bufA, f->Mpad};
     GemmBuf bB{eu->tma_ok ? &f->mapB : nullptr, f->bufB, f->Nc};
@@ -2194,6 +2229,8 @@ int gpb200_fitc_factorize(gpb200_fitc* f, const double* theta, double log_noise)
         g.alpha = 1.0; g.beta = 1.0; g.flags = GEMM_LOWER_ONLY;
         FCK(launch_gemm(es, g));
     }
+    // multi-GPU: Sigma_QR = K_uu + sum over ranks of K_uf L^-1 K_fu  -- the one M x M exchange of the FITC likelihood
+    { int rca = fitc_allreduce(f, es->G, (size_t)f->Mpad * (size_t)f->Mpad); if (rca) return rca; }
     int rc = chol_inplace(es);
     if (rc != GPB200_OK) { f->err = "fitc_factorize (Sigma_QR): " + es->err; return rc; }
     f->factored = true;
@@ -2219,6 +2256,7 @@ int gpb200_fitc_mll(gpb200_fitc* f, const double* y_minus_mean, double* alpha, d
         FCK(rowdot_launch(f->bufB, f->Nc, f->w, f->M, f->Nc, f->tmpm, st));
         FCK(ew_launch(2, f->M, f->bvec, f->tmpm, nullptr, nullptr, 0.0, st));
     }
+    { int rca = fitc_allreduce(f, f->bvec, (size_t)f->Mpad); if (rca) return rca; }              // b summed over the ranks' rows
     // u = Sigma_QR^-1 b   (== get_alpha_u, fitc.jl:279-286)
     FCK(cudaMemcpyAsync(f->rhsm, f->bvec, sizeof(double) * f->Mpad, cudaMemcpyDeviceToDevice, st));
     FCK(solve_device(es, f->rhsm, f->tmpm, f->uvec));
@@ -2236,13 +2274,25 @@ int gpb200_fitc_mll(gpb200_fitc* f, const double* y_minus_mean, double* alpha, d
     FCK(sum_launch(eu->logd, eu->Npad, f->scal + 2, st));
     FCK(ew_launch(4, f->N, f->tmpn, f->lam, nullptr, nullptr, 0.0, st));
     FCK(sum_launch(f->tmpn, f->N, f->scal + 3, st));
-    double s[4];
-    FCK(cudaMemcpyAsync(s, f->scal, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+    double s[5];
+    if (f->nranks > 1) {
+        // r'alpha, sum log Lambda and N are sums over the ranks' rows; the two M x M log-determinants are replicated
+        const double nloc = (double)f->N;
+        FCK(cudaMemcpyAsync(f->scal + 8, f->scal + 0, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        FCK(cudaMemcpyAsync(f->scal + 9, f->scal + 3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        FCK(cudaMemcpyAsync(f->scal + 10, &nloc, sizeof(double), cudaMemcpyHostToDevice, st));
+        { int rca = fitc_allreduce(f, f->scal + 8, 3); if (rca) return rca; }
+        FCK(cudaMemcpyAsync(f->scal + 0, f->scal + 8, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        FCK(cudaMemcpyAsync(f->scal + 3, f->scal + 9, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        FCK(cudaMemcpyAsync(f->scal + 4, f->scal + 10, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    FCK(cudaMemcpyAsync(s, f->scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, st));
     if (alpha) FCK(cudaMemcpyAsync(alpha, f->alpha, sizeof(double) * f->N, cudaMemcpyDeviceToHost, st));
     FCK(cudaStreamSynchronize(st));
+    f->Ntotal = f->nranks > 1 ? s[4] : (double)f->N;
     const double ld = s[1] - s[2] + s[3];
     if (logdet) *logdet = ld;
-    *mll = -(s[0] + ld + LOG2PI * (double)f->N) / 2.0;
+    *mll = -(s[0] + ld + LOG2PI * f->Ntotal) / 2.0;
     f->alpha_ready = true;
     return GPB200_OK;
 }
@@ -2268,6 +2318,7 @@ int gpb200_fitc_grad_noise(gpb200_fitc* f, double* dmll_noise) {
     FCK(dot_launch(f->alpha, f->alpha, f->N, f->scal + 1, st));
     FCK(ew_launch(5, f->N, f->tmpn, f->lam, nullptr, nullptr, 0.0, st));
     FCK(sum_launch(f->tmpn, f->N, f->scal + 2, st));
+    { int rca = fitc_allreduce(f, f->scal, 3); if (rca) return rca; }                             // sums over the ranks' rows
     double s[3];
     FCK(cudaMemcpyAsync(s, f->scal, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
     FCK(cudaStreamSynchronize(st));
@@ -2421,6 +2472,7 @@ int gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel) {
         FCK(rowdot_launch(f->bufB, Nc, f->w, f->M, Nc, f->tmpm, st));
         FCK(ew_launch(2, f->M, f->rhsm, f->tmpm, nullptr, nullptr, 0.0, st));
     }
+    { int rca = fitc_allreduce(f, f->rhsm, (size_t)Mp); if (rca) return rca; }                    // K_uf alpha over all rows
     FCK(solve_device(eu, f->rhsm, f->tmpm, f->betav));
     FCK(cudaMemsetAsync(f->gacc, 0, sizeof(double) * GPB200_MAX_THETA, st));
     FCK(cudaMemsetAsync(f->Hbuf, 0, sizeof(double) * Mp * Mp, st));
@@ -2470,6 +2522,9 @@ int gpb200_fitc_grad_kernel(gpb200_fitc* f, double* dmll_kernel) {
             FCK(launch_gemm(eu, g));
         }
     }
+    // multi-GPU: the per-row traces and H = K_uf diag(g) K_fu are sums over the ranks' rows; the M x M part below is replicated
+    { int rca = fitc_allreduce(f, f->gacc, (size_t)np); if (rca) return rca; }
+    { int rca = fitc_allreduce(f, f->Hbuf, (size_t)Mp * (size_t)Mp); if (rca) return rca; }
     {   // T = K_uu^-1 H ; Wbuf = K_uu^-1 T' = K_uu^-1 H K_uu^-1
         GemmDesc g = gemm_desc_default();
         g.A = GemmOperand{bufG(eu), bufNone(), 0, 0};

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "gpb200_fitc_grad_noise": (C.c_int, [_H, _dp]),
     "gpb200_fitc_grad_kernel": (C.c_int, [_H, _dp]),
     "gpb200_fitc_predict": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp]),
+    "gpb200_fitc_comm_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_char_p]),
     "gpb200_fitc_predict_cov": (C.c_int, [_H, C.c_int64, _dp, C.c_int64, _dp, _dp]),
     "gpb200_fitc_set_mode": (C.c_int, [_H, C.c_int]),
     "gpb200_fitc_launch_count": (C.c_int64, [_H]),
@@ -302,7 +303,7 @@ class Engine:
     # -- multi-GPU (one process per GPU) -------------------------------------------------------
     def nccl_unique_id(self):
         buf = C.create_string_buffer(128)
-        rc = self._lib.gpb200_nccl_unique_id(C.cast(buf, C.c_void_p))
+        rc = (self._lib if self is not None else load_library()).gpb200_nccl_unique_id(C.cast(buf, C.c_void_p))
         if rc != OK:
             raise RuntimeError("gpb200_nccl_unique_id failed (%d)" % rc)
         return buf.raw
@@ -428,6 +429,10 @@ class FitcEngine:
         self._check(self._lib.gpb200_fitc_predict(self._h, Ms, _as_dp(xs_pm), d, _as_dp(mu),
                                                   _as_dp(var) if want_var else None), "fitc_predict")
         return mu, var
+
+    def comm_init(self, nranks, rank, id128):
+        ib = C.create_string_buffer(bytes(id128), 128)
+        self._check(self._lib.gpb200_fitc_comm_init(self._h, int(nranks), int(rank), C.cast(ib, C.c_char_p)), "fitc_comm_init")
 
     def predict_cov(self, xs_pm):
         xs_pm = np.ascontiguousarray(xs_pm, dtype=np.float64)

@@ -15,7 +15,10 @@ from .means import MeanZero
 class FITC:
     _mode = 0
 
-    def __init__(self, x, Xu, y, mean=None, kernel=None, logNoise=-2.0, device=0):
+    def __init__(self, x, Xu, y, mean=None, kernel=None, logNoise=-2.0, device=0, distributed=False):
+        """distributed=True (one process per GPU, torch.distributed initialised): x / y are THIS rank's slice of the observations,
+        Xu / kernel / logNoise are the same everywhere; mll and the gradients are those of the full data set, alpha is the
+        slice's."""
         self.mean = mean if mean is not None else MeanZero()
         self.kernel = kernel
         self.logNoise = float(logNoise)
@@ -27,6 +30,11 @@ class FITC:
             raise ValueError("Input and output observations must have consistent dimensions.")
         self._xpm = np.ascontiguousarray(self.x.T)
         self._eng = capi.FitcEngine(device)
+        if distributed:
+            import torch.distributed as dist
+            from .dist import broadcast_bytes
+            uid = broadcast_bytes(capi.Engine.nccl_unique_id(None) if dist.get_rank() == 0 else None, src=0)
+            self._eng.comm_init(dist.get_world_size(), dist.get_rank(), uid)
         self._eng.set_mode(self._mode)
         self._eng.set_data(self._xpm, np.ascontiguousarray(self.Xu.T))
         ops, dims, theta, exposed = flatten(kernel, self.dim)

@@ -235,6 +235,11 @@ typedef struct gpb200_fitc gpb200_fitc;
 int  gpb200_fitc_create(gpb200_fitc** out, int device);
 void gpb200_fitc_destroy(gpb200_fitc* f);
 const char* gpb200_fitc_last_error(gpb200_fitc* f);
+/* multi-GPU (one process per GPU): after gpb200_nccl_unique_id / broadcast of the id, every rank joins; each rank then passes
+ * ITS OWN slice of the observations to gpb200_fitc_set_data / _mll (alpha is returned for that slice) and the same inducing points
+ * and hyper-parameters.  Exchanged over NCCL: one all-reduce of the M x M accumulator Sigma_QR per factorisation (0.54 GB at
+ * M = 8192), one of H per kernel gradient, M-vectors and scalars; K_uu / Sigma_QR factorisations and predictions are replicated. */
+int  gpb200_fitc_comm_init(gpb200_fitc* f, int nranks, int rank, const char* id128);
 /* x: d x N training inputs, xu: d x M inducing inputs (both column-major, one point per column) */
 int  gpb200_fitc_set_data(gpb200_fitc* f, int64_t N, int32_t d, const double* x, int64_t ldx,
                           int64_t M, const double* xu, int64_t ldxu);
