@@ -2,7 +2,8 @@
 row-sharded Gram + block Cholesky over the ranks (one process per GPU, NCCL over NVLink).  A replicated N x N matrix is
 137 GB: the run is possible only because every rank maps its own block rows (csrc/shard_impl.cuh).
 
-  torchrun --nproc-per-node 8 profiles/tools/run_c4.py [--n 131072] [--d 16] [--m 4096] [--steps 1] [--shard 1]
+  torchrun --nproc-per-node 8 profiles/tools/run_c4.py [--npts 131072] [--dim 16] [--mtest 4096] [--evals 1] [--storage 1]
+  (option names avoid torchrun's own prefixes: its argparse would otherwise claim e.g. --n)
 
 Prints one bench-style JSON line (rank 0): mll+grad time (device events, max over ranks), phases, storage per rank, and
 size-independent parity properties (the oracle cannot run at this size): residual of K_y alpha = y on sampled rows (rows of
@@ -15,13 +16,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gaussianprocess
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=131072)
-    ap.add_argument("--d", type=int, default=16)
-    ap.add_argument("--m", type=int, default=4096)
-    ap.add_argument("--steps", type=int, default=1)
-    ap.add_argument("--shard", type=int, default=1)
-    ap.add_argument("--rb", type=int, default=0)
-    ap.add_argument("--fd", type=int, default=1)
+    ap.add_argument("--npts", type=int, default=131072)
+    ap.add_argument("--dim", type=int, default=16)
+    ap.add_argument("--mtest", type=int, default=4096)
+    ap.add_argument("--evals", type=int, default=1)
+    ap.add_argument("--storage", type=int, default=1)
+    ap.add_argument("--rowblock", type=int, default=0)
+    ap.add_argument("--fdcheck", type=int, default=1)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -31,17 +32,17 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N, d = args.n, args.d
+    N, d = args.npts, args.dim
     rng = np.random.default_rng(4)
     X = rng.standard_normal((N, d)); y = rng.standard_normal(N)
-    Xs = np.random.default_rng(44).standard_normal((args.m, d))
+    Xs = np.random.default_rng(44).standard_normal((args.mtest, d))
     kern = gpb200.Mat32Iso(math.log(2.0), 0.0)
     eng = gpb200.Engine(local)
     if world > 1:
         init_engine_comm(eng, p2p=False)                 # communicator BEFORE the data: storage mode depends on it
-    eng.set_option("shard", args.shard)
-    if args.rb:
-        eng.set_option("shard_rb", args.rb)
+    eng.set_option("shard", args.storage)
+    if args.rowblock:
+        eng.set_option("shard_rb", args.rowblock)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     t0 = time.time()
@@ -63,7 +64,7 @@ def main():
 
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     ms_mll, ms_grad, phases = [], [], None
-    for _ in range(args.steps):
+    for _ in range(args.evals):
         barrier()
         e0.record(stream)
         gp.update_mll()
@@ -92,7 +93,7 @@ def main():
     var_ok = bool(np.all(s2 >= 0) and np.all(s2 <= 1.0 + 1e-12))
     fd_rel = None
     g0 = gp.dmll.copy(); mll0 = gp.mll
-    if args.fd:
+    if args.fdcheck:
         p0 = gp.get_params(); dirv = np.array([0.4, -0.3, 0.5]); h = 1e-4
         gp.set_params(p0 + h * dirv); gp.update_mll(); tp = gp.mll
         gp.set_params(p0 - h * dirv); gp.update_mll(); tm = gp.mll
@@ -104,13 +105,13 @@ def main():
         ms = float(np.median(ms_mll) + np.median(ms_grad))
         line = {
             "metric": "log-mll+grad GFLOP/s, GPE Mat32Iso N=%d d=%d FP64 (update_mll_and_dmll!), row-sharded storage" % (N, d),
-            "value": falg / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms,
+            "value": falg / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "n_gpus": world, "steps": args.evals, "ms_per_step": ms,
             "ms_mll": float(np.median(ms_mll)), "ms_grad": float(np.median(ms_grad)), "higher_is_better": True, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "C4: GPE Mat32Iso(log 2, 0) logNoise 0 MeanZero, N=%d d=%d: Gram + Cholesky + alpha/mll + K^-1 + trace" % (N, d),
                        "parallelism": "%d ranks, F/G row-sharded block-cyclic (rb=%d tiles), NCCL" % (world, info["rb"]),
                        "phases_ms": {k: round(v, 2) for k, v in phases.items() if k in ("gram", "cholesky", "solve_mll", "inverse", "trace")},
-                       "first_update_mll_incl_upload_s": t_first, "predict_f_M%d_ms" % args.m: t_pred, "predict_f_dev_ms": t_pred_dev},
+                       "first_update_mll_incl_upload_s": t_first, "predict_f_M%d_ms" % args.mtest: t_pred, "predict_f_dev_ms": t_pred_dev},
             "storage": {"sharded": info["sharded"], "GB_F_per_rank": info["bytes_F"] / 1e9, "GB_G_per_rank": info["bytes_G"] / 1e9,
                         "GB_one_full_matrix": 8.0 * N * N / 1e9, "tma": info["tma"]},
             "check": {"mll": float(mll0), "dmll": [float(v) for v in g0], "alpha_l1": float(np.sum(np.abs(gp.alpha))),
