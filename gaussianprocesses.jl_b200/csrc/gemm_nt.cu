@@ -43,6 +43,8 @@ struct GemmKP {
     int a_has_sub, b_has_sub;
     int klo_off, bm_mod, bm_rem, bn_mod, bn_rem;
     int bm_div, bm_off, bn_div, bn_off;
+    int own_compact, n_own;      // row-ownership launches: the grid enumerates only the owned tile rows (n_own of them)
+    long long own_first;         // global ordinal of the first owned tile row of this launch
     int gm_tri, k_down;          // rasterisation of triangular (GEMM_KLO_M) launches: group height, descending k
     int n_peer;                  // extra copies of C stored into peer GPUs' buffers (NVLink P2P), same ldc/offsets
     double* Cpeer[7];
@@ -72,7 +74,24 @@ __device__ __forceinline__ TileCtx decode_tile(const GemmKP& p) {
         const int GROUP_M = (p.flags & GEMM_KLO_M) ? p.gm_tri : 16;
         const int tm = p.M / BM, tn = p.N / BN;
         int rem = blockIdx.x;
-        if (!(p.flags & GEMM_LOWER_ONLY)) {
+        if (p.own_compact) {
+            // multi-GPU launches that touch only the tile rows this rank owns (block-cyclic): enumerate exactly those rows,
+            // 8 at a time, column by column inside a group -- no CTA is spent on a foreign row (at 8 ranks 7/8 of a plain
+            // grid would start, decode and exit).  ordinal -> global tile row in closed form.
+            constexpr int GO = 8;
+            const int per_group = GO * tn;
+            const int group = rem / per_group, in_group = rem - group * per_group;
+            const int o = group * GO + in_group % GO;
+            t.bn = in_group / GO;
+            t.bm = 0;
+            if (o < p.n_own) {
+                const long long og = (long long)o + p.own_first;
+                const long long tg = ((og / p.bm_div) * p.bm_mod + p.bm_rem) * p.bm_div + og % p.bm_div;
+                t.bm = (int)(tg - p.bm_off);
+            } else {
+                t.bm = tm;                                     // -> invalid below
+            }
+        } else if (!(p.flags & GEMM_LOWER_ONLY)) {
             const int per_group = GROUP_M * tn;
             const int group = rem / per_group;
             const int first_m = group * GROUP_M;
@@ -436,6 +455,7 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
                       const char* f = getenv("GPB200_K_DOWN"); kd = f ? (atoi(f) != 0) : 1; }
         p.gm_tri = gm; p.k_down = kd;
     }
+    p.own_compact = 0; p.n_own = 0; p.own_first = 0;
     p.n_peer = d.n_peer;
     for (int q = 0; q < 7; ++q) p.Cpeer[q] = q < d.n_peer ? d.Cpeer[q] : nullptr;
     p.alpha = d.alpha; p.beta = d.beta;
@@ -446,6 +466,21 @@ cudaError_t gemm_nt_launch(const GemmDesc& d, int impl, cudaStream_t stream) {
     // one CTA per tile (LOWER_ONLY: per tile of the lower trapezoid), walked in L2-friendly groups
     long long ntiles = (long long)tm * tn;
     if (d.flags & GEMM_LOWER_ONLY) { ntiles = 0; for (int r = 0; r < tm; ++r) ntiles += (r < tn - 1 ? r : tn - 1) + 1; }
+    if (d.bm_mod > 1 && d.batch == 1) {
+        // compact enumeration of the owned tile rows
+        auto own_before = [&](long long t) {
+            const long long cyc = (long long)p.bm_div * d.bm_mod, c = t / cyc, r = t % cyc;
+            long long extra = r - (long long)d.bm_rem * p.bm_div;
+            if (extra < 0) extra = 0;
+            if (extra > p.bm_div) extra = p.bm_div;
+            return c * p.bm_div + extra;
+        };
+        p.own_first = own_before(p.bm_off);
+        p.n_own = (int)(own_before((long long)p.bm_off + tm) - p.own_first);
+        p.own_compact = 1;
+        if (p.n_own <= 0) return cudaSuccess;
+        ntiles = (long long)((p.n_own + 7) / 8) * 8 * tn;
+    }
     dim3 grid((unsigned)ntiles, 1, (unsigned)d.batch);
     if (impl == 0) {
         if (!d.A.buf.map || !d.B.buf.map) return cudaErrorInvalidValue;

@@ -153,6 +153,9 @@ struct gpb200_handle {
     double* Sbuf = nullptr;                    // all-gather staging: nranks regions of S_per_rank doubles; scratch of the inverse sweep
     size_t S_per_rank = 0;
     CUtensorMap mapP[4] = {}, mapXR[2] = {}, mapS{};
+    double* XRbig[2] = {nullptr, nullptr};     // row-panel forms X_J of a BATCH of panels (inverse sweep: batched LAUUM part)
+    int xr_batch = 1;                          // panels per batch
+    CUtensorMap mapXRbig[2] = {};
     double* red = nullptr;                     // small reduction scratch (local group all-reduce)
     int* redi = nullptr;
     struct gpb200_group* grp = nullptr;        // in-process group of virtual ranks on one device (gpb200_group_create)

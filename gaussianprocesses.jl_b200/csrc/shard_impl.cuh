@@ -294,6 +294,7 @@ int shard_pick_rb(gpb200_handle* h) {
 
 void shard_free_buffers(gpb200_handle* h) {
     for (int i = 0; i < 4; ++i) { if (h->P[i]) cudaFree(h->P[i]); h->P[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) { if (h->XRbig[i]) cudaFree(h->XRbig[i]); h->XRbig[i] = nullptr; }
     if (h->Sbuf) cudaFree(h->Sbuf);
     if (h->red) cudaFree(h->red);
     if (h->redi) cudaFree(h->redi);
@@ -353,6 +354,9 @@ int alloc_FG_sharded(gpb200_handle* h) {
     h->S_per_rank = max_own_tiles * TILE * nbp;
     const size_t selems = std::max(h->S_per_rank * (size_t)h->nranks, pelems);
     CK(cudaMalloc(&h->Sbuf, sizeof(double) * selems));
+    // batched LAUUM part of the inverse sweep: up to 4096 columns of row panels at a time (two buffers: look-ahead)
+    h->xr_batch = std::max<int>(1, (int)(4096 / nbp));
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&h->XRbig[i], sizeof(double) * (size_t)h->xr_batch * nbp * Np));
     CK(cudaMalloc(&h->red, sizeof(double) * 4096 * 8));
     CK(cudaMalloc(&h->redi, sizeof(int) * 16));
     h->tma_ok = make_FG_maps(h) &&
@@ -362,7 +366,9 @@ int alloc_FG_sharded(gpb200_handle* h) {
                 gemm_make_tensor_map(&h->mapP[3], h->P[3], Np, nbp, nbp) &&
                 gemm_make_tensor_map(&h->mapXR[0], h->P[1], nbp, Np, Np) &&
                 gemm_make_tensor_map(&h->mapXR[1], h->P[3], nbp, Np, Np) &&
-                gemm_make_tensor_map(&h->mapS, h->Sbuf, Np, nbp, nbp);
+                gemm_make_tensor_map(&h->mapS, h->Sbuf, Np, nbp, nbp) &&
+                gemm_make_tensor_map(&h->mapXRbig[0], h->XRbig[0], (int64_t)h->xr_batch * nbp, Np, Np) &&
+                gemm_make_tensor_map(&h->mapXRbig[1], h->XRbig[1], (int64_t)h->xr_batch * nbp, Np, Np);
     // without TMA descriptors the GEMMs fall back to the plain-load kernel (launch_gemm), storage_info reports it
     return GPB200_OK;
 }
@@ -752,9 +758,17 @@ int shard_inverse_la(const Locals& L) {
     }
     // per local rank: events of the two previous main steps
     std::vector<cudaEvent_t> ev_full1(nl, nullptr), ev_full2(nl, nullptr), ev_trtri1(nl, nullptr), ev_panel(nl, nullptr);
+    // The LAUUM part is applied per BATCH of gB consecutive panels: one panel alone gives N = NBp output columns, i.e. fewer
+    // tiles than SMs with inner dimensions up to Npad -- measured at C2 on 8 GPUs: 200 ms for the sweep, bound by the
+    // duration of a single long-K tile per panel.  The row-panel forms X_J of a batch are collected in XRbig[batch & 1].
+    const int gB = h0->xr_batch;
     for (int k = nblk - 1; k >= 0; --k) {
         const int j0 = k * NBp, nb = std::min(NBp, Np - j0), o = k % R, r1 = j0 + nb;
         const int ncols = Np - r1, set = k & 1;
+        const int bidx = (nblk - 1 - k) / gB;                        // batch of this panel
+        const int k_first = nblk - 1 - bidx * gB, k_low = std::max(0, k_first - gB + 1);
+        const int j0L = k_low * NBp, xb = bidx & 1;
+        const int batch_cols = std::min(Np, (k_first + 1) * NBp) - j0L;
         const int j0p = (k > 0) ? (k - 1) * NBp : 0;                 // start of block k-1 (size NBp)
         // ---------------- chain of panel k ----------------
         for (size_t i = 0; i < nl; ++i) {
@@ -790,7 +804,8 @@ int shard_inverse_la(const Locals& L) {
             for (size_t i = 0; i < nl; ++i) {
                 gpb200_handle* q = L[i];
                 ++q->launches;
-                cudaError_t e = shard_transpose(q->P[2 * set + 1] + j0, Np, q->P[2 * set] + (size_t)j0 * NBp, NBp, Np - j0, nb, q->st);
+                cudaError_t e = shard_transpose(q->XRbig[xb] + (size_t)(j0 - j0L) * Np + j0, Np, q->P[2 * set] + (size_t)j0 * NBp, NBp,
+                                                Np - j0, nb, q->st);
                 if (e == cudaSuccess && k > 0 && q->rank == (k - 1) % R) {
                     // narrow TRTRI update: the accumulator rows of block k-1 (the next panel to be finalised)
                     if (ev_trtri1[i]) e = cudaStreamWaitEvent(q->st, ev_trtri1[i], 0);           // main(k+1)'s TRTRI part adds into the same rows
@@ -829,14 +844,14 @@ int shard_inverse_la(const Locals& L) {
             }
             cudaEvent_t et = ring_event(q);
             SCK(q, cudaEventRecord(et, q->st));
-            {   // LAUUM part of panel k for the own rows >= j0
+            if (k == k_low) {   // LAUUM part of the whole batch [k_low, k_first] for the own rows >= j0L
                 GemmDesc g = gemm_desc_default();
-                g.A = GemmOperand{bufG(q), bufDinvT(q), j0, j0};
-                g.B = GemmOperand{bufXR(q, set), bufNone(), 0, j0};
-                g.C = q->G; g.ldc = q->ld; g.c_row0 = j0; g.c_col0 = j0;
-                g.M = Np - j0; g.N = nb; g.K = Np - j0;
+                g.A = GemmOperand{bufG(q), bufDinvT(q), j0L, j0L};
+                g.B = GemmOperand{GemmBuf{&q->mapXRbig[xb], q->XRbig[xb], q->Npad}, bufNone(), 0, j0L};
+                g.C = q->G; g.ldc = q->ld; g.c_row0 = j0L; g.c_col0 = j0L;
+                g.M = Np - j0L; g.N = batch_cols; g.K = Np - j0L;
                 g.flags = GEMM_LOWER_ONLY | GEMM_KLO_M;
-                own_rows_filter(q, g, j0);
+                own_rows_filter(q, g, j0L);
                 SCK(q, launch_gemm(q, g));
             }
             cudaEvent_t ef = ring_event(q);

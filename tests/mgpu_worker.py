@@ -31,7 +31,7 @@ def main():
         Xs = rng.standard_normal((50, d))
         gp = gpb200.GPE(X.T, y, gpb200.MeanConst(0.2), kern, -0.5, device=local)
         gp._eng.set_option("dist_nb", dist_nb)
-        gp.init_distributed()                       # maps peer memory (fused panel broadcast) when available
+        gp.init_distributed(p2p=True)               # maps peer memory (fused panel broadcast): both panel paths are compared below
         gp.update_target_and_dtarget()
         t_p2p = (gp.mll, gp.dmll.copy())
         gp._eng.set_option("p2p", 0)                # same problem through the NCCL panel broadcast
