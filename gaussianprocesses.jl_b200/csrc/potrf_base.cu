@@ -179,6 +179,93 @@ constexpr int PB = 16;                                     // panel width
 
 __device__ __forceinline__ double& WT(double* S, int m, int j) { return S[j * LDS + m + 1]; }      // W[m][j], m >= j, in the upper part
 
+// 16 x 16 Cholesky in registers, rows across lanes (lane i = lane & 15 holds a[0..15] of row i).  Template recursion keeps every
+// array index a compile-time constant: with plain unrolled loops the compiler kept a[] in local memory (LDL/STL) and the
+// serial block cost ~7 us (ncu source page, profiles/r02_leaf_*): 8 of them were 43 % of the tile.
+template <int J, int K>
+struct Chol16Upd {
+    static __device__ __forceinline__ void run(double (&a)[PB], double lij, int i) {
+        const double lkj = __shfl_sync(0xffffffffu, lij, K);
+        if (i >= K) a[K] = fma(-lij, lkj, a[K]);
+        Chol16Upd<J, K + 1>::run(a, lij, i);
+    }
+};
+template <int J>
+struct Chol16Upd<J, PB> {
+    static __device__ __forceinline__ void run(double (&)[PB], double, int) {}
+};
+template <int J>
+struct Chol16Step {
+    static __device__ __forceinline__ void run(double (&a)[PB], int i, int lane, double* invd, int* info, int pj) {
+        double d = __shfl_sync(0xffffffffu, a[J], J);
+        const bool bad = !(d > 0.0);                          // not positive definite (or NaN): record, keep going
+        if (bad && lane == 0) atomicMin(info, pj + J + 1);
+        d = bad ? 1.0 : d;
+        const double rs = rsqrt(d);
+        const double lij = (i == J) ? d * rs : a[J] * rs;     // L[i][J] for i >= J (0 above the diagonal: a[J] is 0 there)
+        if (i >= J) a[J] = lij;
+        if (lane == J) invd[J] = rs;                          // 1 / L[J][J]
+        Chol16Upd<J, J + 1>::run(a, lij, i);
+        Chol16Step<J + 1>::run(a, i, lane, invd, info, pj);
+    }
+};
+template <>
+struct Chol16Step<PB> {
+    static __device__ __forceinline__ void run(double (&)[PB], int, int, double*, int*, int) {}
+};
+// column c of the inverse of a 16 x 16 lower-triangular block L (rows broadcast from shared memory): x[i], i = 0..15
+template <int I, int M>
+struct Inv16Dot {
+    static __device__ __forceinline__ double run(const double* lrow, const double (&x)[PB], double s) {
+        return Inv16Dot<I, M + 1>::run(lrow, x, fma(-lrow[M], x[M], s));
+    }
+};
+template <int I>
+struct Inv16Dot<I, I> {
+    static __device__ __forceinline__ double run(const double*, const double (&)[PB], double s) { return s; }
+};
+template <int I>
+struct Inv16Row {
+    static __device__ __forceinline__ void run(const double* Lblk, const double* invd, int c, double (&x)[PB]) {
+        const double s = Inv16Dot<I, 0>::run(Lblk + I * LDS, x, (I == c) ? 1.0 : 0.0);
+        x[I] = (I >= c) ? s * invd[I] : 0.0;
+        Inv16Row<I + 1>::run(Lblk, invd, c, x);
+    }
+};
+template <>
+struct Inv16Row<PB> {
+    static __device__ __forceinline__ void run(const double*, const double*, int, double (&)[PB]) {}
+};
+// rank-16 trailing update for the 16-blocks >= T0 (compile-time: the 8 x 8 register tile only carries the live blocks)
+template <int T0>
+__device__ __forceinline__ void trailing_update(double* S, int c0, int ty, int tx) {
+    double acc[8][8];
+#pragma unroll
+    for (int a_ = T0; a_ < 8; ++a_)
+#pragma unroll
+        for (int b_ = T0; b_ < 8; ++b_) acc[a_][b_] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < PB; ++k) {
+        double av[8], bv[8];
+#pragma unroll
+        for (int a_ = T0; a_ < 8; ++a_) av[a_] = S[(ty + PB * a_) * LDS + c0 + k];
+#pragma unroll
+        for (int b_ = T0; b_ < 8; ++b_) bv[b_] = S[(tx + PB * b_) * LDS + c0 + k];
+#pragma unroll
+        for (int a_ = T0; a_ < 8; ++a_)
+#pragma unroll
+            for (int b_ = T0; b_ < 8; ++b_)
+                if (a_ >= b_) acc[a_][b_] = fma(av[a_], bv[b_], acc[a_][b_]);      // blocks above the diagonal are never stored
+    }
+#pragma unroll
+    for (int a_ = T0; a_ < 8; ++a_)
+#pragma unroll
+        for (int b_ = T0; b_ < 8; ++b_) {
+            const int r = ty + PB * a_, c = tx + PB * b_;
+            if (a_ >= b_ && r >= c) S[r * LDS + c] -= acc[a_][b_];
+        }
+}
+
 __global__ void __launch_bounds__(NTB, 1)
 potrf128_blk_kernel(const double* __restrict__ G, long long ldg, double* __restrict__ F, long long ldf,
                     double* __restrict__ Dinv, double* __restrict__ DinvT, double* __restrict__ logd,
@@ -206,23 +293,7 @@ potrf128_blk_kernel(const double* __restrict__ G, long long ldg, double* __restr
             double a[PB];
 #pragma unroll
             for (int k = 0; k < PB; ++k) a[k] = (k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
-#pragma unroll
-            for (int j = 0; j < PB; ++j) {
-                double d = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(d > 0.0)) {                            // not positive definite (or NaN): record, keep going
-                    if (lane == 0) atomicMin(info, p + c0 + j + 1);
-                    d = 1.0;
-                }
-                const double rs = rsqrt(d);
-                const double lij = (i == j) ? d * rs : a[j] * rs;        // L[i][j] for i >= j
-                if (i >= j) a[j] = lij;
-                if (lane == j) invd[c0 + j] = rs;                         // 1 / L[j][j]
-#pragma unroll
-                for (int k = j + 1; k < PB; ++k) {
-                    const double lkj = __shfl_sync(0xffffffffu, lij, k);
-                    if (i >= k) a[k] = fma(-lij, lkj, a[k]);
-                }
-            }
+            Chol16Step<0>::run(a, i, lane, invd + c0, info, p + c0);
             if (lane < PB) {
 #pragma unroll
                 for (int k = 0; k < PB; ++k) if (k <= i) S[(c0 + i) * LDS + c0 + k] = a[k];
@@ -250,33 +321,17 @@ potrf128_blk_kernel(const double* __restrict__ G, long long ldg, double* __restr
         __syncthreads();
         // (c) trailing update S[r][c] -= sum_k L[r][c0+k] L[c][c0+k], r >= c >= c0 + 16: thread (ty, tx) owns rows ty + 16 a, cols tx + 16 b
         {
-            const int t0 = (c0 + PB) / PB;                   // first trailing 16-block index
             const int ty = tid >> 4, tx = tid & 15;
-            double acc[8][8];
-#pragma unroll
-            for (int a_ = 0; a_ < 8; ++a_)
-#pragma unroll
-                for (int b_ = 0; b_ < 8; ++b_) acc[a_][b_] = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < PB; ++k) {
-                double av[8], bv[8];
-#pragma unroll
-                for (int a_ = 0; a_ < 8; ++a_) av[a_] = (a_ >= t0) ? S[(ty + PB * a_) * LDS + c0 + k] : 0.0;
-#pragma unroll
-                for (int b_ = 0; b_ < 8; ++b_) bv[b_] = (b_ >= t0) ? S[(tx + PB * b_) * LDS + c0 + k] : 0.0;
-#pragma unroll
-                for (int a_ = 0; a_ < 8; ++a_)
-#pragma unroll
-                    for (int b_ = 0; b_ < 8; ++b_) acc[a_][b_] = fma(av[a_], bv[b_], acc[a_][b_]);
+            switch (pb + 1) {                                 // first trailing 16-block
+            case 1: trailing_update<1>(S, c0, ty, tx); break;
+            case 2: trailing_update<2>(S, c0, ty, tx); break;
+            case 3: trailing_update<3>(S, c0, ty, tx); break;
+            case 4: trailing_update<4>(S, c0, ty, tx); break;
+            case 5: trailing_update<5>(S, c0, ty, tx); break;
+            case 6: trailing_update<6>(S, c0, ty, tx); break;
+            case 7: trailing_update<7>(S, c0, ty, tx); break;
+            default: break;
             }
-            __syncthreads();                                 // every read of the panel columns is done before the tile changes
-#pragma unroll
-            for (int a_ = 0; a_ < 8; ++a_)
-#pragma unroll
-                for (int b_ = 0; b_ < 8; ++b_) {
-                    const int r = ty + PB * a_, c = tx + PB * b_;
-                    if (a_ >= t0 && b_ >= t0 && r >= c) S[r * LDS + c] -= acc[a_][b_];
-                }
         }
         __syncthreads();
     }
@@ -302,13 +357,7 @@ potrf128_blk_kernel(const double* __restrict__ G, long long ldg, double* __restr
     {
         const int c0 = warp * PB, c = lane & 15;
         double x[PB];
-#pragma unroll
-        for (int i = 0; i < PB; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int m = 0; m < i; ++m) s = fma(-S[(c0 + i) * LDS + c0 + m], x[m], s);
-            x[i] = (i >= c) ? s * invd[c0 + i] : 0.0;
-        }
+        Inv16Row<0>::run(S + c0 * LDS + c0, invd + c0, c, x);
         if (lane < PB) {
 #pragma unroll
             for (int i = 0; i < PB; ++i) W16[(warp * PB + i) * 17 + c] = x[i];
