@@ -236,6 +236,32 @@ template <>
 struct Inv16Row<PB> {
     static __device__ __forceinline__ void run(const double*, const double*, int, double (&)[PB]) {}
 };
+// phase 2, step BK: Acc[r][j] += sum_k L[r][16 BK + k] W[16 BK + k][j] for the row blocks a > BK and column blocks b <= BK
+// (W[m][j] and Acc[m][j] are kept at S[j][m+1]); in the diagonal column block W[16 BK + k][j] = 0 for k < j - 16 BK
+template <int BK>
+__device__ __forceinline__ void inverse_update(double* S, int ty, int tx) {
+    double acc[8][8];
+#pragma unroll
+    for (int a_ = BK + 1; a_ < 8; ++a_)
+#pragma unroll
+        for (int b_ = 0; b_ <= BK; ++b_) acc[a_][b_] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < PB; ++k) {
+        double av[8], bv[8];
+#pragma unroll
+        for (int a_ = BK + 1; a_ < 8; ++a_) av[a_] = S[(ty + PB * a_) * LDS + PB * BK + k];
+#pragma unroll
+        for (int b_ = 0; b_ <= BK; ++b_) bv[b_] = (b_ == BK && k < tx) ? 0.0 : S[(tx + PB * b_) * LDS + PB * BK + k + 1];
+#pragma unroll
+        for (int a_ = BK + 1; a_ < 8; ++a_)
+#pragma unroll
+            for (int b_ = 0; b_ <= BK; ++b_) acc[a_][b_] = fma(av[a_], bv[b_], acc[a_][b_]);
+    }
+#pragma unroll
+    for (int a_ = BK + 1; a_ < 8; ++a_)
+#pragma unroll
+        for (int b_ = 0; b_ <= BK; ++b_) S[(tx + PB * b_) * LDS + ty + PB * a_ + 1] += acc[a_][b_];
+}
 // rank-16 trailing update for the 16-blocks >= T0 (compile-time: the 8 x 8 register tile only carries the live blocks)
 template <int T0>
 __device__ __forceinline__ void trailing_update(double* S, int c0, int ty, int tx) {
@@ -370,24 +396,39 @@ potrf128_blk_kernel(const double* __restrict__ G, long long ldg, double* __restr
         if (i >= j) WT(S, b * PB + i, b * PB + j) = W16[(b * PB + i) * 17 + j];
     }
     __syncthreads();
-    // block rows 1..7:  T = L[bi, 0:16 bi] W[0:16 bi, 0:16 bi];  W[bi, 0:16 bi] = -W16[bi] T
+    // right-looking over row blocks: the accumulators Acc[i][j] = sum_k L[i][k] W[k][j] of the off-diagonal blocks live where
+    // W[i][j] will be (upper part of S, zero so far).  Step bk: finalise row block bk (W = -W16[bk] Acc), then every row block
+    // below receives the rank-16 contribution L[., bk] W[bk, .] with an 8 x 8 register tile per thread.
 #pragma unroll 1
-    for (int bi = 1; bi < T / PB; ++bi) {
-        const int r0 = bi * PB, ncol = r0;
-        for (int o = tid; o < PB * ncol; o += NTB) {
-            const int i = o / ncol, j = o - i * ncol;        // j fastest: W column reads are conflict-free, L row reads broadcast
-            const double* lrow = S + (r0 + i) * LDS;
-            double s = 0.0;
-            for (int k = j; k < ncol; ++k) s = fma(lrow[k], WT(S, k, j), s);
-            Tb[i * LDS + j] = s;
-        }
-        __syncthreads();
-        for (int o = tid; o < PB * ncol; o += NTB) {
-            const int i = o / ncol, j = o - i * ncol;
-            double s = 0.0;
+    for (int bk = 0; bk < T / PB; ++bk) {
+        const int r0 = bk * PB;
+        if (bk > 0) {
+            for (int j = tid; j < r0; j += NTB) {                 // one thread per column j < 16 bk
+                double x[PB], w[PB];
 #pragma unroll
-            for (int k = 0; k < PB; ++k) if (k <= i) s = fma(W16[(r0 + i) * 17 + k], Tb[k * LDS + j], s);
-            WT(S, r0 + i, j) = -s;
+                for (int i = 0; i < PB; ++i) x[i] = WT(S, r0 + i, j);
+#pragma unroll
+                for (int i = 0; i < PB; ++i) {
+                    double acc_ = 0.0;
+#pragma unroll
+                    for (int k = 0; k <= i; ++k) acc_ = fma(W16[(r0 + i) * 17 + k], x[k], acc_);
+                    w[i] = -acc_;
+                }
+#pragma unroll
+                for (int i = 0; i < PB; ++i) WT(S, r0 + i, j) = w[i];
+            }
+            __syncthreads();
+        }
+        const int ty = tid >> 4, tx = tid & 15;
+        switch (bk) {
+        case 0: inverse_update<0>(S, ty, tx); break;
+        case 1: inverse_update<1>(S, ty, tx); break;
+        case 2: inverse_update<2>(S, ty, tx); break;
+        case 3: inverse_update<3>(S, ty, tx); break;
+        case 4: inverse_update<4>(S, ty, tx); break;
+        case 5: inverse_update<5>(S, ty, tx); break;
+        case 6: inverse_update<6>(S, ty, tx); break;
+        default: break;
         }
         __syncthreads();
     }
