@@ -1120,7 +1120,12 @@ int gpb200_set_option(gpb200_handle* h, const char* key, int64_t value) {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(h, GPB200_EINVAL, "shard_rb must be 0 (auto), 1, 2, 4 or 8");
         h->shard_rb_opt = (int)value; h->factored = h->inv_ready = false; return GPB200_OK;
     }
-    if (!strcmp(key, "trsv_fused")) { h->trsv_fused = value ? 1 : 0; return GPB200_OK; }
+    if (!strcmp(key, "trsv_fused")) {            // 0: one launch per block step; 1: round-1 single-launch kernels; 2 (default): resident-tile kernels
+        if (value < 0 || value > 2) return fail(h, GPB200_EINVAL, "trsv_fused must be 0, 1 or 2");
+        h->trsv_fused = value ? 1 : 0;
+        if (value) trsv_set_variant((int)value);
+        return GPB200_OK;
+    }
     if (!strcmp(key, "p2p")) {                 // 0: NCCL panel broadcast even if peer memory is mapped
         if (value && h->n_peer == 0) return fail(h, GPB200_ESTATE, "p2p: ipc_import first");
         h->p2p = value != 0; return GPB200_OK;

@@ -307,6 +307,7 @@ potrf128_blk_kernel(const double* __restrict__ G, long long ldg, double* __restr
         const int m = idx >> 7, n = idx & 127;
         S[m * LDS + n] = (n <= m) ? G[(long long)(p + m) * ldg + p + n] : 0.0;
     }
+    if (tid < T) S[tid * LDS + T] = 0.0;                  // column 128 holds W[127][.]: the phase-2 accumulators start from zero
     __syncthreads();
 
     // ------------------------------- phase 1: Cholesky, 16-column panels -------------------------------

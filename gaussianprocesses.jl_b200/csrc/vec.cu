@@ -11,6 +11,7 @@
 //  * predictive mean / variance epilogues (/root/reference/src/GP.jl:26, 51-54, 75).
 #include "vec.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 constexpr int T = 128;
@@ -393,7 +394,127 @@ __global__ void __launch_bounds__(256) trsv_bwd_persistent(const double* __restr
     __syncthreads();
     if (threadIdx.x == 0) st_release(flags + b, 1);
 }
+// ---- version 2 of the single-launch solves: the two tiles on the critical chain are RESIDENT before the CTA starts waiting --
+// the inverted diagonal tile in registers (each thread keeps exactly the 16 x 4 entries its part of the tile mat-vec uses) and
+// the neighbour tile L[b, b-1] (forward) / L[b+1, b] (backward) in shared memory.  Per block step the chain is then: flag ->
+// 1 KB vector -> mat-vec out of shared memory -> mat-vec out of registers -> flag, instead of two 128 KB tile reads from L2
+// (round 1: 19 us per step, 4.8 + 5.9 ms at C2, the same at every GPU count).  128 KB of dynamic shared memory per CTA: one
+// CTA per SM; later CTAs start as earlier ones retire, dependencies only point to lower blockIdx (in-order dispatch).
+__device__ __forceinline__ void load_tile_regs(const double* __restrict__ M, long long ld, double (&t)[16][4]) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+        const double* row = M + (long long)(w * 16 + rr) * ld;
+        t[rr][0] = row[l]; t[rr][1] = row[l + 32]; t[rr][2] = row[l + 64]; t[rr][3] = row[l + 96];
+    }
+}
+__device__ __forceinline__ void tile_matvec_regs(const double (&t)[16][4], const double* v, double* out) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const double v0 = v[l], v1 = v[l + 32], v2 = v[l + 64], v3 = v[l + 96];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+        double s = t[rr][0] * v0 + t[rr][1] * v1 + t[rr][2] * v2 + t[rr][3] * v3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (l == 0) out[w * 16 + rr] = s;
+    }
+}
+__device__ __forceinline__ void stage_tile_smem(double* dst, const double* __restrict__ M, long long ld) {
+    // 128 x 128 tile, row-major in shared memory with the same 128-double pitch (rows are read by consecutive lanes)
+    for (int idx = threadIdx.x; idx < T * T / 2; idx += blockDim.x) {
+        const int r = idx >> 6, c2 = (idx & 63) * 2;
+        *reinterpret_cast<double2*>(dst + r * T + c2) = *reinterpret_cast<const double2*>(M + (long long)r * ld + c2);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) trsv_fwd_persistent2(const double* __restrict__ F, long long ldf, const double* __restrict__ Dinv,
+                                                               const double* __restrict__ r, double* __restrict__ y,
+                                                               int* __restrict__ flags, int* __restrict__ err) {
+    extern __shared__ __align__(16) double sTile[];            // L[b, b-1]
+    __shared__ double sAcc[T], sY[T], sO[T];
+    __shared__ int ok;
+    const int b = blockIdx.x;
+    const long long q = (long long)b * T;
+    double dreg[16][4];
+    load_tile_regs(Dinv + q * T, T, dreg);
+    if (b > 0) stage_tile_smem(sTile, F + q * ldf + (q - T), ldf);
+    if (threadIdx.x < T) sAcc[threadIdx.x] = r[q + threadIdx.x];
+    __syncthreads();
+    for (int i = 0; i < b; ++i) {
+        if (threadIdx.x == 0) ok = wait_flag(flags + i, err) ? 1 : 0;
+        __syncthreads();
+        if (!ok) return;
+        if (threadIdx.x < T) sY[threadIdx.x] = __ldcg(y + (long long)i * T + threadIdx.x);
+        __syncthreads();
+        if (i == b - 1) tile_matvec(sTile, T, sY, sO);
+        else tile_matvec(F + q * ldf + (long long)i * T, ldf, sY, sO);
+        __syncthreads();
+        if (threadIdx.x < T) sAcc[threadIdx.x] -= sO[threadIdx.x];
+        __syncthreads();
+    }
+    tile_matvec_regs(dreg, sAcc, sO);                         // y_b = W_bb (r_b - sum_i L_bi y_i)
+    __syncthreads();
+    if (threadIdx.x < T) y[q + threadIdx.x] = sO[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flags + b, 1);
+}
+
+__global__ void __launch_bounds__(256, 1) trsv_bwd_persistent2(const double* __restrict__ F, long long ldf, const double* __restrict__ DinvT,
+                                                               const double* __restrict__ z, double* __restrict__ a,
+                                                               int* __restrict__ flags, int* __restrict__ err, int nb) {
+    extern __shared__ __align__(16) double sTile[];            // L[b+1, b]
+    __shared__ double sAcc[T], sA[T], sO[T], sC[T];
+    __shared__ int ok;
+    const int b = nb - 1 - blockIdx.x;                     // dependencies (blocks > b) have lower blockIdx
+    const long long q = (long long)b * T;
+    double dreg[16][4];
+    load_tile_regs(DinvT + q * T, T, dreg);
+    if (b + 1 < nb) stage_tile_smem(sTile, F + (q + T) * ldf + q, ldf);
+    if (threadIdx.x < T) sAcc[threadIdx.x] = z[q + threadIdx.x];
+    __syncthreads();
+    for (int i = nb - 1; i > b; --i) {
+        if (threadIdx.x == 0) ok = wait_flag(flags + i, err) ? 1 : 0;
+        __syncthreads();
+        if (!ok) return;
+        if (threadIdx.x < T) sA[threadIdx.x] = __ldcg(a + (long long)i * T + threadIdx.x);
+        __syncthreads();
+        if (i == b + 1) tile_matvec_t(sTile, T, sA, sO, sC);
+        else tile_matvec_t(F + (long long)i * T * ldf + q, ldf, sA, sO, sC);     // L[i-block, b-block]' a_i
+        __syncthreads();
+        if (threadIdx.x < T) sAcc[threadIdx.x] -= sO[threadIdx.x];
+        __syncthreads();
+    }
+    tile_matvec_regs(dreg, sAcc, sO);                         // a_b = W_bb' (z_b - sum_i L_ib' a_i)
+    __syncthreads();
+    if (threadIdx.x < T) a[q + threadIdx.x] = sO[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flags + b, 1);
+}
+bool g_trsv2_attr = false;
+int g_trsv_variant = -1;
 }  // namespace
+
+// GPB200_TRSV=1 selects the round-1 kernels (critical tiles prefetched to L2 only); default: resident-tile kernels
+static bool trsv_use_v2() {
+    if (g_trsv_variant < 0) {
+        const char* e = getenv("GPB200_TRSV");
+        g_trsv_variant = e ? atoi(e) : 2;
+    }
+    if (g_trsv_variant != 2) return false;
+    if (!g_trsv2_attr) {
+        if (cudaFuncSetAttribute(trsv_fwd_persistent2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * T * T)) != cudaSuccess ||
+            cudaFuncSetAttribute(trsv_bwd_persistent2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * T * T)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            g_trsv_variant = 1;
+            return false;
+        }
+        g_trsv2_attr = true;
+    }
+    return true;
+}
+void trsv_set_variant(int v) { g_trsv_variant = (v == 2) ? 2 : 1; }
 
 // flags: int[Npad/128 + 1] scratch (last entry = watchdog error flag); returns cudaErrorLaunchFailure-free:
 // the caller reads flags[nb] after the stream sync.
@@ -402,6 +523,11 @@ cudaError_t trsv_lower_fwd_fused(const double* F, int64_t ldf, const double* Din
     const int nb = (int)(Npad / T);
     cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (nb + 1), st);
     if (e != cudaSuccess) return e;
+    if (trsv_use_v2()) {
+        trsv_fwd_persistent2<<<nb, 256, sizeof(double) * T * T, st>>>(F, ldf, Dinv, r, y, flags, flags + nb);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
     trsv_fwd_persistent<<<nb, 256, 0, st>>>(F, ldf, Dinv, r, y, flags, flags + nb);
     if (launches) ++*launches;
     return cudaGetLastError();
@@ -411,6 +537,11 @@ cudaError_t trsv_lower_bwd_fused(const double* F, int64_t ldf, const double* Din
     const int nb = (int)(Npad / T);
     cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (nb + 1), st);
     if (e != cudaSuccess) return e;
+    if (trsv_use_v2()) {
+        trsv_bwd_persistent2<<<nb, 256, sizeof(double) * T * T, st>>>(F, ldf, DinvT, z, a, flags, flags + nb, nb);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
     trsv_bwd_persistent<<<nb, 256, 0, st>>>(F, ldf, DinvT, z, a, flags, flags + nb, nb);
     if (launches) ++*launches;
     return cudaGetLastError();

@@ -165,7 +165,8 @@ int64_t gpb200_launch_count(gpb200_handle* h);
  *   "nb"         outer Cholesky block: 0 (default) = fully recursive, else 128*2^k <= 4096 (right-looking panels)
  *   "gemm"       0 = TMA/mbarrier DMMA kernel (default), 1 = simple-loader kernel (bring-up / cross-check)
  *   "lookahead"  1 (default) = next diagonal tile factored on a side stream behind the Schur update
- *   "trsv_fused" 1 (default) = single-launch flag-synchronised triangular solves, 0 = one launch per block step
+ *   "trsv_fused" single-launch flag-synchronised triangular solves: 2 (default) = critical tiles resident in registers / shared
+ *                memory, 1 = round-1 kernels (L2 prefetch only), 0 = one launch per block step
  *   "profile"    1 = CUDA events around every GEMM launch (see gpb200_get_timings)
  *   "dist_nb"    multi-GPU: width of an owned block column, 0 = auto (~N/(8*ranks))
  *   "p2p"        multi-GPU: 1 = fused panel push over peer memory (after gpb200_ipc_import), 0 = NCCL broadcast

@@ -440,3 +440,24 @@ def test_blocked_diagonal_tile_kernel_matches_column_kernel(engine):
         assert abs(ld - np.linalg.slogdet(Ky)[1]) <= 1e-11 * abs(ld)
         assert np.max(np.abs(Kinv @ Ky - np.eye(1000))) <= 1e-9
     assert _rel(out[1][0], out[0][0]) < 1e-12
+
+
+def test_triangular_solve_variants_agree(engine):
+    """alpha = K_y^-1 r (src/GPE.jl:208) through the three schedules of the blocked solves: one launch per block step,
+    the round-1 single-launch kernels, and the resident-tile single-launch kernels (diagonal tile in registers, neighbour
+    tile in shared memory) -- same arithmetic order, so the results agree to the last bits; all match the oracle."""
+    import gpb200
+    X, y, _ = make_data(3000, 3, 51)
+    k = gpb200.SEIso(0.2, 0.1) + gpb200.Mat12Iso(0.5, -0.4)
+    theta, _ = _setup(engine, k, X, nb=0, gemm=0)
+    engine.factorize(theta, -0.9)
+    o = orc.fit(k.spec(), X, y, -0.9)
+    res = {}
+    for v in (0, 1, 2):
+        engine.set_option("trsv_fused", v)
+        alpha, mll = engine.mll(y)
+        res[v] = (alpha, mll, engine.solve(np.cos(X[:, 1])))
+        assert _rel(alpha, o["alpha"]) < RTOL and abs(mll - o["mll"]) <= RTOL * abs(o["mll"])
+    engine.set_option("trsv_fused", 2)
+    for v in (0, 1):
+        assert _rel(res[v][0], res[2][0]) < 1e-13 and _rel(res[v][2], res[2][2]) < 1e-13
