@@ -170,10 +170,12 @@ potrf128_inv_kernel(const double* __restrict__ G, long long ldg, double* __restr
 //            register tiles per thread, 16 shared-memory loads per 64 FMAs.
 //   phase 2: the 16 x 16 diagonal blocks are inverted (one warp per block, one column per lane), then W = L^-1 is built block
 //            row by block row:  W[i, j] = -W_ii * sum_{j <= k < i} L[i, k] W[k, j]  (two small products per block row).
-// ~34 barriers per tile instead of 256 and N^3/6-class FMA counts instead of N^3/2.  MEASURED (B200, round 2,
-// profiles/r02_leaf_durations.csv): 128 us per tile, no better than the 125 us of the column-per-barrier kernel -- the
-// serial 16 x 16 block factorisation on one warp and the dependent accumulations of phase 2 dominate -- so it is NOT the
-// default (option "leaf" = 1 / GPB200_LEAF=1 selects it); kept as the starting point for the next tuning pass.
+// ~40 barriers per tile instead of 256 and N^3/6-class FMA counts instead of N^3/2.  MEASURED on B200 (round 2, ncu
+// gpu__time_duration, profiles/r02_leaf_durations*.csv): first version 128 us (no better than the 123 us column kernel: the
+// 16 x 16 block was kept in local memory by the compiler and phase 2 was a chain of dependent shared-memory dot products) ->
+// 95 us with the template-recursive register block -> 74.5 us with the register-tiled right-looking phase 2.  Cholesky phase
+// at C2: 366.7 ms vs 377.1 ms with the column kernel.  Default since then; option "leaf" = 0 / GPB200_LEAF=0 selects the
+// column kernel (cross-check).
 constexpr int NTB = 256;
 constexpr int PB = 16;                                     // panel width
 
@@ -464,9 +466,9 @@ cudaError_t potrf128_launch(const double* G, int64_t ldg, double* F, int64_t ldf
         if (e != cudaSuccess) return e;
         g_attr_set = true;
     }
-    if (g_leaf_variant < 0) {                              // GPB200_LEAF=1 selects the blocked kernel (default: column-per-barrier kernel)
+    if (g_leaf_variant < 0) {                              // GPB200_LEAF=0 selects the column-per-barrier kernel (default: blocked kernel)
         const char* e = getenv("GPB200_LEAF");
-        g_leaf_variant = e ? (atoi(e) != 0) : 0;
+        g_leaf_variant = e ? (atoi(e) != 0) : 1;
     }
     if (g_leaf_variant) {
         const size_t smb = (size_t)(T * LDS + 8 * PB * 17 + PB * LDS + T) * sizeof(double);

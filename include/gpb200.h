@@ -172,8 +172,8 @@ int64_t gpb200_launch_count(gpb200_handle* h);
  *   "p2p"        multi-GPU: 1 = fused panel push over peer memory (after gpb200_ipc_import), 0 = NCCL broadcast
  *   "gram_fast"  1 (default) = TMA-staged SEIso Gram / trace kernels (gram_fast.cu) when the kernel is one SEIso leaf over
  *                <= 8 dimensions, 0 = always the generic kernel-program kernels (cross-check)
- *   "leaf"       0 (default) = column-per-barrier 128 x 128 diagonal-tile kernel, 1 = blocked kernel with 16-column panels
- *                (measured equally fast on B200; process-wide)
+ *   "leaf"       1 (default) = blocked 128 x 128 diagonal-tile kernel (16-column panels, 74.5 us), 0 = column-per-barrier kernel
+ *                (123 us; cross-check); process-wide
  *   "capacity"   rows reserved by the next gpb200_set_data (>= N) so that gpb200_append can extend the factor in place
  *   "shard"      multi-GPU storage of the two N x N buffers: 1 = row-sharded (each rank maps only its own block rows),
  *                0 = replicated, -1 (default) = sharded only when the replicated form would not fit the device
