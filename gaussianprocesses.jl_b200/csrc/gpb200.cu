@@ -1061,7 +1061,10 @@ void gpb200_destroy(gpb200_handle* h) {
     if (h->grp) {                              // a group dissolves with its first destroyed member
         gpb200_group* g = h->grp;
         for (auto* m : g->hs) { if (m->st) cudaStreamSynchronize(m->st); }
-        for (auto* m : g->hs) { m->grp = nullptr; m->factored = m->inv_ready = false; }
+        for (auto* m : g->hs) {                 // the survivors become ordinary single-rank handles (storage re-allocated at their next factorize)
+            m->grp = nullptr; m->nranks = 1; m->rank = 0;
+            m->factored = m->inv_ready = m->alpha_ready = false;
+        }
         delete g;
     }
     if (h->st) cudaStreamSynchronize(h->st);
@@ -1988,6 +1991,7 @@ int gpb200_nccl_unique_id(char* id128) {
 int gpb200_comm_init(gpb200_handle* h, int nranks, int rank, const char* id128) {
     if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return GPB200_EINVAL;
     if (nranks & (nranks - 1)) return fail(h, GPB200_EINVAL, "comm_init: number of ranks must be a power of two");
+    if (h->grp) return fail(h, GPB200_ESTATE, "comm_init: handle belongs to an in-process group");
     if (!nccl_load()) return fail(h, GPB200_ENCCL, "libnccl.so.2 could not be loaded");
     CK(cudaSetDevice(h->device));
     if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
