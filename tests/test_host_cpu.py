@@ -190,3 +190,109 @@ def test_gpe_push_and_fit_rebuild_state():
     assert gp.mll == pytest.approx(o["mll"], rel=1e-12)
     with pytest.raises(ValueError):
         gp.push(np.zeros((3, 1)), [0.0])
+
+
+class OracleEngineCV(OracleEngine):
+    """OracleEngine plus the round-2 entry points the host mirror drives (cv_param, cv_block, inverse_diag, rand, append,
+    set_option) -- backed by numpy, TEST ONLY: exercises the host-side assembly of crossvalidation.jl / GPEelastic.jl."""
+
+    def __init__(self):
+        super().__init__()
+        self.options = {}
+        self.appended = 0
+
+    def set_option(self, key, value):
+        self.options[key] = value
+
+    def _Kinv(self):
+        Ky = orc.gram(self.spec, self.X, self.ln)
+        return np.linalg.inv(Ky)
+
+    def inverse_diag(self):
+        return np.diag(self._Kinv()).copy()
+
+    def cv_param(self, param, alpha=None):
+        Kinv = self._Kinv()
+        a = self.f["alpha"] if alpha is None else alpha
+        if param < 0:
+            Zj = Kinv
+        else:
+            _, grads = orc.cov_and_grads(self.spec, self.X, None, want_grad=True)
+            Zj = Kinv @ grads[param]
+        self._M = Zj @ Kinv
+        return Zj @ a, np.diag(self._M).copy()
+
+    def cv_block(self, which, idx):
+        M = self._Kinv() if which == 0 else self._M
+        return M[np.ix_(idx, idx)].copy()
+
+    def rand(self, xs, z, nugget=1e-10, alpha=None):
+        mu, cov = orc.predict_f(self.spec, self.X, self.f, xs, full_cov=True)
+        L = np.linalg.cholesky(cov + nugget * np.eye(xs.shape[0]))
+        return mu, mu[None, :] + z @ L.T
+
+    def append(self, xnew):
+        if self.N + xnew.shape[0] > self.options.get("capacity", 0):
+            raise ValueError("append: capacity exceeded")
+        self.X = np.vstack([self.X, xnew]); self.N = self.X.shape[0]
+        self.appended += 1
+
+
+def _gp_cv(kernel, mean, ln, X, y, **kw):
+    eng = OracleEngineCV()
+    gp = gpb200.GPE.__new__(gpb200.GPE)
+    eng.bind(gp)
+    gpb200.GPE.__init__(gp, X.T, y, mean, kernel, ln, engine=eng, **kw)
+    return gp, eng
+
+
+def test_crossvalidation_host_assembly_matches_oracle():
+    """dlogpdθ_LOO / predict_CVfold / logp_CVfold / dlogpdθ_CVfold (src/crossvalidation.jl:67-341): the O(N) / per-fold host
+    assembly of gpe.py over the device's two vectors and sub-blocks equals the oracle's literal restatement."""
+    X, y, _ = make_data(60, 2, 12)
+    k = gpb200.SEIso(0.2, 0.1) + gpb200.fix(gpb200.Mat32Iso(0.4, -0.3), "lσ")
+    gp, eng = _gp_cv(k, gpb200.MeanZero(), -0.6, X, y)
+    gp.update_target_and_dtarget()
+    f = orc.fit(k.spec(), X, y, -0.6)
+    mu, s2 = gp.predict_LOO()
+    mo, so = orc.predict_loo(f, y)
+    assert np.allclose(mu, mo, rtol=1e-9) and np.allclose(s2, so, rtol=1e-9)
+    assert gp.logp_LOO() == pytest.approx(orc.logp_loo(f, y), rel=1e-10)
+    assert np.allclose(gp.dlogp_LOO(), orc.dlogp_loo(k.spec(), X, y, f, -0.6), rtol=1e-8, atol=1e-10)
+    assert gp.dlogp_LOO(noise=False).size == 3 and gp.dlogp_LOO(kern=False).size == 1
+    folds = [np.arange(0, 20), np.arange(20, 45), np.arange(45, 60)]
+    mus, Sigs = gp.predict_CVfold(folds)
+    muo, Sigo = orc.predict_cvfold(f, y, folds)
+    assert all(np.allclose(a, b, rtol=1e-8) for a, b in zip(mus, muo)) and all(np.allclose(a, b, rtol=1e-8) for a, b in zip(Sigs, Sigo))
+    assert gp.logp_CVfold(folds) == pytest.approx(orc.logp_cvfold(f, y, folds), rel=1e-9)
+    assert np.allclose(gp.dlogp_CVfold(folds), orc.dlogp_cvfold(k.spec(), X, y, f, -0.6, folds), rtol=1e-7, atol=1e-9)
+    gpm, _ = _gp_cv(k, gpb200.MeanConst(0.1), -0.6, X, y)
+    with pytest.raises(NotImplementedError):                  # "I don't know how to do means yet" (crossvalidation.jl:168)
+        gpm.dlogp_LOO(domean=True)
+
+
+def test_elastic_append_and_rand_host_logic():
+    """ElasticGPE append! (GPEelastic.jl:13-22): in-place extension inside the capacity, refit with `stepsize` more room beyond
+    it, dimension / length checks; rand (GP.jl:120-146): shape (npred, n), mean function added to every draw."""
+    X, y, Xs = make_data(40, 2, 3, m=5)
+    k = gpb200.SEIso(0.1, 0.2)
+    gp, eng = _gp_cv(k, gpb200.MeanConst(0.5), -1.0, X[:20], y[:20], capacity=30, stepsize=16)
+    assert eng.options["capacity"] == 30
+    gp.append(X[20:26].T, y[20:26])
+    assert eng.appended == 1 and gp.nobs == 26 and gp.alpha.size == 26
+    o = orc.fit(k.spec(), X[:26], y[:26], -1.0, ("MeanConst", 0.5))
+    assert gp.mll == pytest.approx(o["mll"], rel=1e-12)       # update_target!(gp, kern=false, noise=false) on the longer y
+    gp.append(X[26:40].T, y[26:40])                           # 40 > capacity 30: refit with 40 + stepsize reserved
+    assert eng.appended == 1 and gp.nobs == 40 and eng.options["capacity"] == 40 + 16
+    o = orc.fit(k.spec(), X, y, -1.0, ("MeanConst", 0.5))
+    assert gp.mll == pytest.approx(o["mll"], rel=1e-12)
+    with pytest.raises(ValueError):
+        gp.append(np.zeros((3, 1)), [0.0])
+    with pytest.raises(ValueError):
+        gp.append(np.zeros((2, 3)), [0.0, 1.0])
+    draws = gp.rand(Xs.T, 7, rng=np.random.default_rng(0))
+    assert draws.shape == (5, 7)
+    z = np.random.default_rng(0).standard_normal((7, 5))
+    mu_f, cov = orc.predict_f(k.spec(), X, o, Xs, ("MeanConst", 0.5), full_cov=True)
+    want = mu_f[None, :] + z @ np.linalg.cholesky(cov + 1e-10 * np.eye(5)).T
+    assert np.allclose(draws.T, want, rtol=1e-9, atol=1e-10)
