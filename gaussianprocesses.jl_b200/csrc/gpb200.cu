@@ -82,6 +82,7 @@ struct gpb200_handle {
     int gram_fast = 1;                         // option "gram_fast": 0 = always the generic kernels of gram.cu
     // cross-validation (gpb200_cv_*): K_y^-1 mirrored to a full symmetric matrix in G; two N x N temporaries
     bool g_sym = false;
+    bool cv_m_ok = false;                                       // cvD holds M_j = Z_j K^-1 of the last cv_param call
     double *cvD = nullptr, *cvY = nullptr;
     CUtensorMap mapCvD{}, mapCvY{};
     double* cvblk = nullptr; long long* cvidx = nullptr; int64_t cvblk_cap = 0;
@@ -291,7 +292,7 @@ void free_data(gpb200_handle* h) {
     if (h->cvY) cudaFree(h->cvY);
     if (h->cvblk) cudaFree(h->cvblk);
     if (h->cvidx) cudaFree(h->cvidx);
-    h->cvD = h->cvY = h->cvblk = nullptr; h->cvidx = nullptr; h->cvblk_cap = 0; h->g_sym = false;
+    h->cvD = h->cvY = h->cvblk = nullptr; h->cvidx = nullptr; h->cvblk_cap = 0; h->g_sym = false; h->cv_m_ok = false;
     for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
     if (h->info_dev) { cudaFree(h->info_dev); h->info_dev = nullptr; }
     if (h->flags) { cudaFree(h->flags); h->flags = nullptr; }
@@ -1289,7 +1290,7 @@ int gpb200_factorize(gpb200_handle* h, const double* theta, const double* log_no
     for (int i = 0; i < h->prog.n_theta; ++i)
         if (!isfinite(theta[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite hyper-parameter");
     CK(cudaSetDevice(h->device));
-    h->factored = h->inv_ready = h->alpha_ready = false; h->g_sym = false;
+    h->factored = h->inv_ready = h->alpha_ready = false; h->g_sym = false; h->cv_m_ok = false;
     std::vector<double> nv((size_t)n_noise);
     for (int64_t i = 0; i < n_noise; ++i) {
         if (!isfinite(log_noise[i])) return fail(h, GPB200_EINVAL, "factorize: non-finite logNoise");
@@ -1441,7 +1442,7 @@ int gpb200_grad_prepare(gpb200_handle* h) {
     if (!h) return GPB200_EINVAL;
     if (!h->factored) return fail(h, GPB200_ESTATE, "grad_prepare: factorize first");
     if (h->inv_ready) return GPB200_OK;
-    h->g_sym = false;
+    h->g_sym = false; h->cv_m_ok = false;
     CK(cudaSetDevice(h->device));
     CK(cudaEventRecord(h->ev0, h->st));
     if (h->sharded) {
@@ -1700,7 +1701,7 @@ int gpb200_append(gpb200_handle* h, int64_t k, const double* xnew, int64_t ldx) 
                      gemm_make_tensor_map_plain(&h->mapXT, h->xpt, h->dxp, Nnew, Np, h->dxp, TILE);
     }
     h->N = Nnew;
-    h->inv_ready = h->alpha_ready = false; h->g_sym = false;
+    h->inv_ready = h->alpha_ready = false; h->g_sym = false; h->cv_m_ok = false;
     const int init = INT_MAX;
     CK(cudaMemcpyAsync(h->info_dev, &init, sizeof(int), cudaMemcpyHostToDevice, h->st));
     ++h->launches;
@@ -1752,9 +1753,16 @@ static int cv_prepare(gpb200_handle* h) {
     if (!h->inv_ready) return fail(h, GPB200_ESTATE, "cv: grad_prepare first (K_y^-1 must be resident)");
     if (h->nranks > 1) return fail(h, GPB200_ESTATE, "cv: K^-1 is distributed over the ranks; single-GPU handles only");
     const size_t nn = sizeof(double) * (size_t)h->Npad * (size_t)h->Npad;
-    if (!h->cvD) {
-        CK(cudaMalloc(&h->cvD, nn));
-        CK(cudaMalloc(&h->cvY, nn));
+    if (!h->cvD || !h->cvY) {
+        if (h->cvD) { cudaFree(h->cvD); h->cvD = nullptr; }
+        if (h->cvY) { cudaFree(h->cvY); h->cvY = nullptr; }
+        h->cv_m_ok = false;
+        if (cudaMalloc(&h->cvD, nn) != cudaSuccess || cudaMalloc(&h->cvY, nn) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (h->cvD) { cudaFree(h->cvD); h->cvD = nullptr; }
+            h->cvY = nullptr;
+            return fail(h, GPB200_ECUDA, "cv: out of device memory for the two N x N work matrices");
+        }
         if (h->tma_ok && !(gemm_make_tensor_map(&h->mapCvD, h->cvD, h->Npad, h->Npad, h->Npad) &&
                            gemm_make_tensor_map(&h->mapCvY, h->cvY, h->Npad, h->Npad, h->Npad)))
             return fail(h, GPB200_ECUDA, "cv: cuTensorMapEncodeTiled failed");
@@ -1799,6 +1807,7 @@ int gpb200_cv_param(gpb200_handle* h, int32_t param, const double* alpha, double
         g.C = h->cvD; g.ldc = h->Npad; g.M = Np; g.N = Np; g.K = Np;
         CK(launch_gemm(h, g));
     }
+    h->cv_m_ok = true;
     CK(cudaMemcpyAsync(Zj_alpha, h->r1, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(diag_ZjSinv, h->y1, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -1811,6 +1820,7 @@ int gpb200_cv_block(gpb200_handle* h, int32_t which, int64_t nV, const int64_t* 
     CK(cudaSetDevice(h->device));
     int rc = cv_prepare(h);
     if (rc) return rc;
+    if (which == 1 && !h->cv_m_ok) return fail(h, GPB200_ESTATE, "cv_block: which = 1 reads M_j of the last cv_param call; call cv_param first");
     for (int64_t a = 0; a < nV; ++a)
         if (idx[a] < 0 || idx[a] >= h->N) return fail(h, GPB200_EINVAL, "cv_block: index out of range");
     if (nV > h->cvblk_cap) {
