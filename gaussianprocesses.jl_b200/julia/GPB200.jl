@@ -19,7 +19,9 @@ import Random
 import GaussianProcesses: CovarianceStrategy, KernelData, EmptyData, alloc_cK, update_cK!, init_precompute,
                           precompute!, dmll_kern!, dmll_noise, predictMVN, predict_f, predict_full,
                           AbstractGradientPrecompute, Kernel, Mean, GPE, get_params, num_params, mean,
-                          SumKernel, ProdKernel, Masked, FixedKernel
+                          SumKernel, ProdKernel, Masked, FixedKernel, update_target!, get_value,
+                          predict_LOO, predict_CVfold, dlogpdθ_LOO, dlogpdθ_CVfold, Folds
+using ElasticArrays: ElasticArray
 import PDMats: AbstractPDMat, dim
 import Base: \, size, Matrix
 import LinearAlgebra: logdet, tr
@@ -34,8 +36,10 @@ const OP_SUM, OP_PROD = 32, 33
 
 struct B200Covariance <: CovarianceStrategy
     device::Int
+    capacity::Int                 # rows reserved on the device for append! (0: exactly nobs) -- ElasticCovStrat, GPEelastic.jl:3-6
+    stepsize::Int                 # extra rows reserved whenever append! outgrows the reservation
 end
-B200Covariance() = B200Covariance(0)
+B200Covariance(device::Int = 0; capacity::Int = 0, stepsize::Int = 10^3) = B200Covariance(device, capacity, stepsize)
 
 mutable struct B200PDMat <: AbstractPDMat{Float64}
     handle::Ptr{Cvoid}
@@ -46,11 +50,15 @@ mutable struct B200PDMat <: AbstractPDMat{Float64}
     xsize::Tuple{Int,Int}
     ops::Vector{Int32}            # kernel program last sent (skip gpb200_set_kernel while the tree shape is unchanged)
     dims::Vector{Int32}
-    function B200PDMat(device::Int, n::Int)
+    capacity::Int                 # rows reserved on the device (option "capacity"); append! extends in place below it
+    function B200PDMat(device::Int, n::Int, capacity::Int = 0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:gpb200_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
         rc == 0 || error("gpb200_create: ", unsafe_string(ccall((:gpb200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
-        obj = new(h[], n, Int[], 0, UInt(0), (0, 0), Int32[], Int32[])
+        obj = new(h[], n, Int[], 0, UInt(0), (0, 0), Int32[], Int32[], capacity)
+        if capacity > 0
+            ccall((:gpb200_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), h[], "capacity", capacity)
+        end
         finalizer(o -> ccall((:gpb200_destroy, LIB), Cvoid, (Ptr{Cvoid},), o.handle), obj)
         return obj
     end
@@ -104,7 +112,7 @@ end
 # ---- strategy methods (SURVEY.md §8(b); exemplar src/sparse/subsetofregressors.jl) --------------
 KernelData(k::Kernel, X1::AbstractMatrix, X2::AbstractMatrix, ::B200Covariance) = EmptyData()   # no N x N host cache
 
-alloc_cK(cs::B200Covariance, nobs) = B200PDMat(cs.device, nobs)                                 # src/GP.jl:14-20
+alloc_cK(cs::B200Covariance, nobs) = B200PDMat(cs.device, nobs, cs.capacity)                               # src/GP.jl:14-20
 
 size(a::B200PDMat) = (a.n, a.n)
 size(a::B200PDMat, i::Int) = a.n
@@ -182,6 +190,120 @@ function GaussianProcesses.predict_LOO(cK::B200PDMat, alpha::AbstractVector{<:Re
     check(cK, ccall((:gpb200_get_inverse_diag, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), cK.handle, d), "get_inverse_diag")
     σi2 = 1 ./ d
     return -alpha .* σi2 .+ y, σi2
+end
+
+# ---- cross-validation on the device's resident inverse (src/crossvalidation.jl:67-341) -------------------------------
+# The reference forms inv(Σ) and, per hyper-parameter j, Z_j = inv(Σ) ∂K_j and Z_j inv(Σ) on the host (three N x N
+# matrices, two N^3 products).  Here K_y^-1 is already resident after gpb200_grad_prepare: gpb200_cv_param returns the two
+# N-vectors every formula needs (Z_j α and diag(Z_j inv(Σ)); j = -1 is the noise direction, Z = inv(Σ)) and gpb200_cv_block
+# reads the principal sub-blocks the fold formulas index.  The O(N) / per-fold assembly below is the reference's, line by line.
+function cv_param(cK::B200PDMat, j::Integer, alpha::AbstractVector)
+    Zjα = Vector{Float64}(undef, cK.n); dg = Vector{Float64}(undef, cK.n)
+    check(cK, ccall((:gpb200_cv_param, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    cK.handle, j, Vector{Float64}(alpha), Zjα, dg), "cv_param")
+    return Zjα, dg
+end
+
+# which = 0: inv(Σ)[V,V];  which = 1: (Z_j inv(Σ))[V,V] of the last cv_param call.  Both are symmetric, so the row-major
+# block the device writes is the column-major matrix Julia reads.
+function cv_block(cK::B200PDMat, which::Integer, V::AbstractVector{Int})
+    idx = Vector{Int64}(V .- 1); B = Matrix{Float64}(undef, length(V), length(V))
+    check(cK, ccall((:gpb200_cv_block, LIB), Cint, (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Ptr{Float64}),
+                    cK.handle, which, length(V), idx, B), "cv_block")
+    return B
+end
+
+# one parameter of dlogpdθ_LOO_kern! / dlogpdσ2_LOO (crossvalidation.jl:86-101, 119-131), before the factor -1/2
+function loo_component(y, alpha, σi2, μi, Zjα, ZjΣinv)
+    ∂σ2 = ZjΣinv .* (σi2 .^ 2)
+    ∂μ = Zjα .* σi2 .- alpha .* ∂σ2
+    return -sum(2 .* (y .- μi) ./ σi2 .* ∂μ) - sum((y .- μi) .^ 2 .* ZjΣinv) + sum(ZjΣinv .* σi2)
+end
+
+function dlogpdθ_LOO(gp::GPE{X,Y,M,K,CS,D,P}; noise::Bool, domean::Bool, kern::Bool) where {X,Y,M,K,CS<:B200Covariance,D,P}
+    cK = gp.cK; y = gp.y; alpha = gp.alpha
+    n_mean_params = num_params(gp.mean)
+    domean && n_mean_params > 0 && throw("I don't know how to do means yet")       # crossvalidation.jl:162
+    μi, σi2 = predict_LOO(cK, alpha, y)                                             # runs gpb200_grad_prepare
+    out = Float64[]
+    if noise                                                                        # crossvalidation.jl:157-160
+        Zjα, dg = cv_param(cK, -1, alpha)
+        push!(out, -loo_component(y, alpha, σi2, μi, Zjα, dg) / 2 * 2 * exp(2 * get_value(gp.logNoise)))
+    end
+    if kern
+        for j in cK.exposed                                                         # FixedKernel selection, fixed_kernel.jl:64-66
+            Zjα, dg = cv_param(cK, j - 1, alpha)
+            push!(out, -loo_component(y, alpha, σi2, μi, Zjα, dg) / 2)
+        end
+    end
+    return out
+end
+
+function predict_CVfold(cK::B200PDMat, alpha::AbstractVector{<:Real}, y::AbstractVector{<:Real}, folds::Folds)   # crossvalidation.jl:180-191
+    check(cK, ccall((:gpb200_grad_prepare, LIB), Cint, (Ptr{Cvoid},), cK.handle), "grad_prepare")
+    μ = Vector{Float64}[]; Σ = Matrix{Float64}[]
+    for V in folds
+        ΣVT = inv(Symmetric(cv_block(cK, 0, V)))
+        push!(μ, y[V] - ΣVT * alpha[V]); push!(Σ, Matrix(ΣVT))
+    end
+    return μ, Σ
+end
+
+# gradient_fold (crossvalidation.jl:250-261) with the two sub-blocks read off the device
+function fold_component(cK::B200PDMat, alpha, Zjα, V, ΣVTinv)
+    ZVV = cv_block(cK, 1, V)
+    C = cholesky(Symmetric(ΣVTinv))
+    ΣVTα = C \ alpha[V]
+    return -2 * dot(ΣVTα, Zjα[V]) + dot(ΣVTα, ZVV * ΣVTα) + tr(C \ ZVV)
+end
+
+function dlogpdθ_CVfold(gp::GPE{X,Y,M,K,CS,D,P}, folds::Folds; noise::Bool, domean::Bool, kern::Bool) where {X,Y,M,K,CS<:B200Covariance,D,P}
+    cK = gp.cK; alpha = gp.alpha
+    n_mean_params = num_params(gp.mean)
+    domean && n_mean_params > 0 && throw("I don't know how to do means yet")       # crossvalidation.jl:330
+    check(cK, ccall((:gpb200_grad_prepare, LIB), Cint, (Ptr{Cvoid},), cK.handle), "grad_prepare")
+    blocks = [cv_block(cK, 0, V) for V in folds]                                    # inv(Σ)[V,V], shared by every parameter
+    out = Float64[]
+    if noise
+        Zjα, _ = cv_param(cK, -1, alpha)
+        push!(out, -sum(fold_component(cK, alpha, Zjα, V, B) for (V, B) in zip(folds, blocks)) / 2 * 2 * exp(2 * get_value(gp.logNoise)))
+    end
+    if kern
+        for j in cK.exposed
+            Zjα, _ = cv_param(cK, j - 1, alpha)
+            push!(out, -sum(fold_component(cK, alpha, Zjα, V, B) for (V, B) in zip(folds, blocks)) / 2)
+        end
+    end
+    return out
+end
+
+# ---- ElasticGPE on the device (src/GPEelastic.jl:13-22, 38-47) ------------------------------------------------------
+# B200Covariance(device; capacity, stepsize) reserves rows on the device so that append! extends the Cholesky factor in place
+# (gpb200_append: O(k N^2)) instead of refitting; beyond the reservation the data is refitted with `stepsize` more rows
+# reserved, which is what ElasticPDMats' resize! amounts to.
+function B200ElasticGPE(x::AbstractMatrix, y::AbstractVector, mean::Mean, kernel::Kernel, logNoise::Real = -2.0;
+                        device::Int = 0, capacity::Int = 10^3, stepsize::Int = 10^3)
+    return GPE(ElasticArray(Matrix{Float64}(x)), ElasticArray(Vector{Float64}(y)), mean, kernel, logNoise,
+               B200Covariance(device; capacity = capacity, stepsize = stepsize))
+end
+
+Base.append!(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractVector, y::Float64) where {X,Y,M,K,CS<:B200Covariance,D,P<:B200PDMat} =
+    append!(gp, reshape(x, :, 1), [y])
+function Base.append!(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractMatrix, y::AbstractVector) where {X,Y,M,K,CS<:B200Covariance,D,P<:B200PDMat}
+    size(x, 2) == length(y) || error("$(size(x, 2)) observations, but $(length(y)) targets.")       # GPEelastic.jl:14
+    cK = gp.cK; k = length(y)
+    Xn = Matrix{Float64}(x)
+    inplace = get_value(gp.logNoise) isa Real && cK.n + k <= cK.capacity
+    append!(gp.x, Xn); append!(gp.y, y); gp.nobs += k
+    if inplace
+        check(cK, ccall((:gpb200_append, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64), cK.handle, k, Xn, size(Xn, 1)), "append")
+        cK.n += k; cK.xid = objectid(gp.x); cK.xsize = size(gp.x)
+        return update_target!(gp, kern = false, noise = false)                                      # GPEelastic.jl:21
+    end
+    cK.capacity = gp.nobs + gp.covstrat.stepsize
+    check(cK, ccall((:gpb200_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), cK.handle, "capacity", cK.capacity), "set_option")
+    cK.xid = UInt(0)                                                                                # force the upload of the grown x
+    return update_target!(gp)
 end
 
 # batched prediction instead of the per-column loop of src/GP.jl:72-76
@@ -324,6 +446,6 @@ function predict_f(gp::GPE{X,Y,M,K,CS,D,P}, x::AbstractMatrix; full_cov::Bool=fa
     return mu .+ mean(gp.mean, Xs), max.(var, 0.0)
 end
 
-export B200Covariance, B200Sparse
+export B200Covariance, B200Sparse, B200ElasticGPE
 
 end # module

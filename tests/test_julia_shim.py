@@ -66,7 +66,7 @@ def julia_ccalls():
 
 C2JL = {"int": {"Cint"}, "int32_t": {"Int32", "Cint"}, "int64_t": {"Int64"}, "double": {"Float64", "Cdouble"},
         "const double*": {"Ptr{Float64}", "Ref{Float64}"}, "double*": {"Ptr{Float64}", "Ref{Float64}"},
-        "const int32_t*": {"Ptr{Int32}"}, "gpb200_handle*": {"Ptr{Cvoid}"}, "gpb200_fitc*": {"Ptr{Cvoid}"},
+        "const int32_t*": {"Ptr{Int32}"}, "const int64_t*": {"Ptr{Int64}"}, "int64_t*": {"Ptr{Int64}"}, "gpb200_handle*": {"Ptr{Cvoid}"}, "gpb200_fitc*": {"Ptr{Cvoid}"},
         "gpb200_handle**": {"Ref{Ptr{Cvoid}}"}, "gpb200_fitc**": {"Ref{Ptr{Cvoid}}"}, "const char*": {"Cstring", "Ptr{UInt8}"},
         "char*": {"Ptr{UInt8}"}, "void*": {"Ptr{Cvoid}"}}
 
@@ -117,3 +117,23 @@ def test_dense_update_ck_is_typed_like_the_reference_pair():
     body = src[src.index("function predictMVN("):]
     body = body[:body.index("\nend\n")]
     assert "error(" not in body and "predict_raw" in body
+
+
+def test_shim_binds_the_crossvalidation_and_elastic_entry_points():
+    """crossvalidation.jl:142,180,311 and GPEelastic.jl:13 get device-backed methods: each is imported from the reference
+    module (so the definitions EXTEND its generic functions) and reaches its C entry point."""
+    src = open(JL).read()
+    bound = {c[0] for c in julia_ccalls()}
+    for sym in ("gpb200_cv_param", "gpb200_cv_block", "gpb200_append", "gpb200_rand", "gpb200_set_option",
+                "gpb200_get_inverse_diag", "gpb200_fitc_predict_cov"):
+        assert sym in bound, sym
+    imports = src[src.index("import GaussianProcesses:"):src.index("import PDMats")]
+    for fn in ("predict_LOO", "predict_CVfold", "dlogpdθ_LOO", "dlogpdθ_CVfold", "Folds", "update_target!", "get_value"):
+        assert fn in re.split(r"[\s,:]+", imports), fn
+    for sig in (r"function dlogpdθ_LOO\(gp::GPE\{X,Y,M,K,CS,D,P\}; noise::Bool, domean::Bool, kern::Bool\)",
+                r"function predict_CVfold\(cK::B200PDMat, alpha::AbstractVector\{<:Real\}, y::AbstractVector\{<:Real\}, folds::Folds\)",
+                r"function dlogpdθ_CVfold\(gp::GPE\{X,Y,M,K,CS,D,P\}, folds::Folds; noise::Bool, domean::Bool, kern::Bool\)",
+                r"function Base\.append!\(gp::GPE\{X,Y,M,K,CS,D,P\}, x::AbstractMatrix, y::AbstractVector\)"):
+        assert re.search(sig, src), sig
+    # 0-based parameter / row indices cross the ABI (include/gpb200.h), 1-based ones stay in Julia
+    assert "cv_param(cK, j - 1, alpha)" in src and "Vector{Int64}(V .- 1)" in src
