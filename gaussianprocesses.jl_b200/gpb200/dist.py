@@ -44,3 +44,24 @@ def max_over_ranks(value):
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def partition_bounds(m, world):
+    """contiguous, balanced split of m items over `world` ranks: rank r owns [b[r], b[r+1])"""
+    return [(m * r) // world for r in range(world + 1)]
+
+
+def allgather_concat(local, counts):
+    """Every rank passes its float64 vector (length counts[rank]); every rank gets the concatenation in rank order.
+    Device-side for nccl, host for gloo (only O(M) result values travel -- the data path stays inside the engine)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    width = max(max(counts), 1)
+    buf = torch.zeros(width, dtype=torch.float64, device=dev)
+    if local.size:
+        buf[:local.size] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
+    outs = [torch.empty_like(buf) for _ in counts]
+    dist.all_gather(outs, buf)
+    return np.concatenate([o[:c].cpu().numpy() for o, c in zip(outs, counts)])

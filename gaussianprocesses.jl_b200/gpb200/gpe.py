@@ -194,17 +194,40 @@ class GPE:
         return self
 
     # ---- prediction ----------------------------------------------------------------------
-    def predict_f(self, x, full_cov=False):
-        """predict_f(gp, x; full_cov) (src/GP.jl:64-79), batched on the device."""
+    def predict_f(self, x, full_cov=False, partition=False):
+        """predict_f(gp, x; full_cov) (src/GP.jl:64-79), batched on the device.
+        partition=True (multi-GPU, replicated storage): every rank holds the whole factor, so the test points are split
+        over the ranks -- each engine predicts its contiguous slice, independent of the others -- and the O(M) results are
+        all-gathered; every rank returns the full vectors.  (Row-sharded storage predicts collectively instead: the
+        triangular solve itself is distributed, see shard_predict_solve.)"""
         x = _as_dxn(x)
         if x.shape[0] != self.dim:
             raise ValueError("Gaussian Process object and input observations do not have consistent dimensions")
         xs = np.ascontiguousarray(x.T)
+        if partition and getattr(self, "_world", 1) > 1:
+            return self._predict_f_partitioned(xs, full_cov)
         mu, var, cov = self._eng.predict(xs, None, want_var=not full_cov, full_cov=full_cov)
         mu = mu + self.mean.mean(xs)
         if full_cov:
             return mu, cov
         return mu, np.maximum(var, 0.0)                            # GP.jl:75
+
+    def _predict_f_partitioned(self, xs, full_cov):
+        import torch.distributed as tdist
+        from .dist import partition_bounds, allgather_concat
+        if full_cov:
+            raise ValueError("predict_f(partition=True): the full covariance couples all test points; use partition=False")
+        if self._eng.storage_info()["sharded"]:
+            raise ValueError("predict_f(partition=True) needs replicated storage; the row-sharded predict is collective")
+        world, rank = tdist.get_world_size(), tdist.get_rank()
+        b = partition_bounds(xs.shape[0], world)
+        counts = [b[r + 1] - b[r] for r in range(world)]
+        if counts[rank]:
+            mu, var, _ = self._eng.predict(xs[b[rank]:b[rank + 1]], None, want_var=True, full_cov=False)
+        else:
+            mu, var = np.empty(0), np.empty(0)
+        mu = allgather_concat(mu, counts) + self.mean.mean(xs)
+        return mu, np.maximum(allgather_concat(var, counts), 0.0)                # GP.jl:75
 
     def predict_y(self, x, full_cov=False):                        # GPE.jl:408-416
         mu, s2 = self.predict_f(x, full_cov=full_cov)
